@@ -1,0 +1,203 @@
+/*
+ * sbench_b200.h -- C ABI of the B200-native (sm_100a) backend for GridTools'
+ * stencil_benchmarks ("sbench").
+ *
+ * This header is the drop-in boundary.  Every entry point below replaces one
+ * FFI surface of the reference's GPU backend (paths relative to the reference
+ * tree, `sb/` = stencil_benchmarks/, `sb/bc/` = sb/benchmarks_collection/):
+ *
+ *   - the JIT-compiled `extern "C" int kernel(double* time, T* f0, ..., T* fn)`
+ *     of sb/bc/stencils/cuda_hip/templates/base.j2:68-193, called through
+ *     ctypes from sb/bc/stencils/cuda_hip/mixin.py:162-175;
+ *   - the `extern "C" int run()` of sb/bc/stream/cuda_hip.j2:179-288, called
+ *     from sb/bc/stream/cuda_hip.py:121-144;
+ *   - the libcudart calls the reference makes through ctypes for device
+ *     memory (sb/bc/stencils/cuda_hip/api.py:39-104).
+ *
+ * Conventions kept from the reference (sb/tools/compilation.py:155-196):
+ *   - every function returns int, 0 = success; on failure a one-line reason
+ *     is written to stderr, the sticky CUDA error is cleared and 1 is returned;
+ *   - field pointers are DEVICE pointers to the FIRST INTERIOR element
+ *     (sb/tools/compilation.py:273-282 with offset = halo); the halo lies at
+ *     negative offsets; strides are in ELEMENTS, in (i, j, k) order
+ *     (sb/bc/stencils/base.py:119-121);
+ *   - `time` (seconds) is measured with CUDA events around ONE sweep after
+ *     `dry_runs` untimed sweeps (base.j2:137-184).  If `time` is NULL the
+ *     sweep is only enqueued on `stream` (no events, no synchronisation), so
+ *     a caller can time a batch itself or capture it in a CUDA graph.
+ *
+ * Differences from the reference ABI, on purpose:
+ *   - geometry, dtype and dry_runs are run-time arguments of a pre-built
+ *     library instead of literals baked into a JIT-compiled source;
+ *   - an explicit `stream` (a cudaStream_t passed as void*, NULL = default
+ *     stream) so halo exchange can overlap the interior sweep.
+ *
+ * No torch types, no C++ types: plain pointers and sizes only.
+ */
+#ifndef SBENCH_B200_H
+#define SBENCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* dtype codes (NumPy names used by the `dtype` Parameter, sb/bc/stencils/base.py:53) */
+#define SB200_F32 0
+#define SB200_F64 1
+
+/* basic stencil kinds (sb/bc/stencils/base.py:175-254) */
+#define SB200_BASIC_EMPTY 0
+#define SB200_BASIC_COPY 1
+#define SB200_BASIC_ONESIDED_AVG 2
+#define SB200_BASIC_SYMMETRIC_AVG 3
+#define SB200_BASIC_LAPLACIAN 4
+
+/* STREAM operations (sb/bc/stream/cuda_hip.j2:132-173) */
+#define SB200_STREAM_COPY 0  /* c = a          */
+#define SB200_STREAM_SCALE 1 /* b = s * c      */
+#define SB200_STREAM_ADD 2   /* c = a + b      */
+#define SB200_STREAM_TRIAD 3 /* a = b + s * c  */
+#define SB200_STREAM_INIT 4  /* a = 1, b = 2, c = 0 */
+
+/* vadv storage variants for the Thomas coefficients */
+#define SB200_VADV_AUTO 0
+#define SB200_VADV_GLOBAL 1 /* ccol/dcol round trip through HBM (reference "classic") */
+#define SB200_VADV_ONCHIP 2 /* coefficients stay in shared memory / tensor memory    */
+
+/* ------------------------------------------------------------------ */
+/* Runtime (replaces sb/bc/stencils/cuda_hip/api.py:39-104)            */
+/* ------------------------------------------------------------------ */
+
+/* Library version as major*10000 + minor*100 + patch. Never fails. */
+int sb200_version(void);
+
+/* cudaGetDeviceCount; 0 devices is not an error here. */
+int sb200_device_count(int* count);
+
+/* cudaSetDevice / cudaGetDevice (base.j2:75-78 uses the current device). */
+int sb200_set_device(int device);
+int sb200_get_device(int* device);
+
+/* Name, SM count, global memory bytes and L2 bytes of the current device. */
+int sb200_device_info(char* name, int name_len, int* sm_count,
+                      uint64_t* global_mem_bytes, uint64_t* l2_bytes);
+
+/* cudaMalloc / cudaFree (api.py:54-78). */
+int sb200_malloc(void** dptr, size_t nbytes);
+int sb200_free(void* dptr);
+
+/* Pinned host memory (cudaHostAlloc / cudaFreeHost) for the host fields, and
+ * registration of memory that is already allocated (cudaHostRegister). */
+int sb200_host_alloc(void** hptr, size_t nbytes);
+int sb200_host_free(void* hptr);
+int sb200_host_register(void* hptr, size_t nbytes);
+int sb200_host_unregister(void* hptr);
+
+/* cudaMemcpyAsync on `stream` followed by a stream synchronise when `sync`
+ * is non-zero (api.py:80-93 + device_synchronize :95-96). */
+int sb200_memcpy_h2d(void* dptr, const void* hptr, size_t nbytes, void* stream, int sync);
+int sb200_memcpy_d2h(void* hptr, const void* dptr, size_t nbytes, void* stream, int sync);
+int sb200_memcpy_d2d(void* dst, const void* src, size_t nbytes, void* stream, int sync);
+int sb200_memset(void* dptr, int value, size_t nbytes, void* stream, int sync);
+
+/* cudaStreamSynchronize(stream) (stream == NULL: cudaDeviceSynchronize). */
+int sb200_synchronize(void* stream);
+
+/* Evict the L2 by overwriting a scratch buffer larger than the L2. */
+int sb200_flush_l2(void* stream);
+
+/* Number of sb200 kernels launched by this process so far (for bench.py's
+ * `gpu_launches` claim). */
+uint64_t sb200_launch_count(void);
+
+/* ------------------------------------------------------------------ */
+/* STREAM (replaces `run()` of sb/bc/stream/cuda_hip.j2:179-288)       */
+/* ------------------------------------------------------------------ */
+
+/* Full McCalpin-style run on device arrays owned by the library: init
+ * (a=1, b=2, c=0), `ntimes` rounds of copy/scale/add/triad each timed with
+ * events, iteration 0 discarded, table printed to stdout in the reference's
+ * format ("Copy: <MB/s> <avg> <min> <max>", cuda_hip.j2:262-275), closed-form
+ * verification (cuda_hip.j2:290-345) when `verify` != 0.  Returns non-zero on
+ * a CUDA error or failed verification. */
+int sb200_stream_run(int dtype, uint64_t array_size, int ntimes, int verify);
+
+/* One STREAM operation on caller-owned device arrays of `n` elements, scalar
+ * 3 as in the reference unless given.  Arrays must be 16-byte aligned.
+ * `time` as described at the top. */
+int sb200_stream_op(int op, int dtype, void* a, void* b, void* c, uint64_t n,
+                    double scalar, int dry_runs, double* time, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Stencils (replace `kernel()` of cuda_hip/templates/base.j2:68-193)  */
+/* ------------------------------------------------------------------ */
+
+/* Geometry arguments shared by all stencil entry points:
+ *   nx, ny, nz   interior domain (sb/bc/stencils/base.py:46)
+ *   sx, sy, sz   element strides of the padded field (base.py:119-121);
+ *                sx must be 1 (layout (2,1,0): i is the unit-stride axis)
+ * All fields of one stencil share the strides (they come from the same
+ * allocator call with the same parameters, base.py:87-109). */
+
+/* Basic stencils (bodies: sb/bc/stencils/cuda_hip/basic.py:101-132; oracle:
+ * sb/bc/stencils/base.py:180-254).
+ *   kind    SB200_BASIC_*
+ *   axis    averaged axis 0/1/2 (one-sided: +1 neighbour; symmetric: +-1)
+ *   along   bit mask of Laplacian axes: bit0 = x, bit1 = y, bit2 = z
+ * Only interior points of `out` are written. */
+int sb200_basic(int kind, int dtype, const void* inp, void* out,
+                int64_t nx, int64_t ny, int64_t nz,
+                int64_t sx, int64_t sy, int64_t sz,
+                int axis, int along, int dry_runs, double* time, void* stream);
+
+/* Horizontal diffusion (oracle: sb/bc/stencils/base.py:276-311; reference GPU
+ * variants: sb/bc/stencils/cuda_hip/horizontal_diffusion.py:50-128).  One
+ * fused kernel: Laplacian -> flx/fly -> limiter -> update.  Needs a halo of at
+ * least 2 in i and j around `inp` (base.py:261-264).  `inp` and `coeff` are
+ * never written; only interior points of `out` are written. */
+int sb200_hdiff(int dtype, const void* inp, const void* coeff, void* out,
+                int64_t nx, int64_t ny, int64_t nz,
+                int64_t sx, int64_t sy, int64_t sz,
+                int dry_runs, double* time, void* stream);
+
+/* Vertical advection, u component (oracle: sb/bc/stencils/base.py:349-501 with
+ * all_components=False; reference GPU variants:
+ * sb/bc/stencils/cuda_hip/vertical_advection.py:60-73).  Per-(i,j)-column Thomas
+ * solve, k-sequential.  `utensstage` is read and overwritten; `ccol`/`dcol`
+ * are scratch (contents unspecified afterwards, as in the reference, base.py:485-501)
+ * and may be NULL for the on-chip variant; `datacol` is never touched and may
+ * be NULL.  Needs a halo of at least 1 in i around `wcon` (base.py:324-327).
+ *   ishift, jshift   which wcon neighbour enters gav/gcv: (1,0) for u,
+ *                    (0,1) for v, (0,0) for w (base.py:475-483)
+ *   variant          SB200_VADV_*  */
+int sb200_vadv(int dtype, const void* ustage, const void* upos, const void* utens,
+               void* utensstage, const void* wcon, void* ccol, void* dcol, void* datacol,
+               int64_t nx, int64_t ny, int64_t nz,
+               int64_t sx, int64_t sy, int64_t sz,
+               int ishift, int jshift, int variant,
+               int dry_runs, double* time, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Multi-GPU halo plumbing for the J-partitioned horizontal diffusion  */
+/* ------------------------------------------------------------------ */
+
+/* Pack `nrows` consecutive j-rows (all nz levels, i range [-hx, nx+hx)) of a
+ * field into a contiguous buffer / unpack them again, so that one
+ * ncclSend/ncclRecv moves a whole halo face.  `field` points to the first
+ * interior element, `j0` is the first row relative to it (negative = halo).
+ * Buffer layout: [k][row][i] with nx + 2*hx elements per row. */
+int sb200_pack_rows(int dtype, const void* field, void* buffer,
+                    int64_t nx, int64_t nz, int64_t hx,
+                    int64_t sy, int64_t sz, int64_t j0, int64_t nrows, void* stream);
+int sb200_unpack_rows(int dtype, void* field, const void* buffer,
+                      int64_t nx, int64_t nz, int64_t hx,
+                      int64_t sy, int64_t sz, int64_t j0, int64_t nrows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SBENCH_B200_H */

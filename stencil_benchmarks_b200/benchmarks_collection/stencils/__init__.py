@@ -1,0 +1,1 @@
+from . import b200  # noqa: F401

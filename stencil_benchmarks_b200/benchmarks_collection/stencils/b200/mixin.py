@@ -1,0 +1,199 @@
+"""Backend mixin of the B200 stencils: host fields, device mirrors, C-ABI calls.
+
+Counterpart of the reference's ``cuda_hip.StencilMixin``
+(stencil_benchmarks/benchmarks_collection/stencils/cuda_hip/mixin.py:50-175):
+
+=====================  =====================================================
+reference               here
+=====================  =====================================================
+render Jinja + nvcc     pre-built ``libsbench_b200.so`` (sm_100a only); a
+at ``setup()``          missing library is a ``ParameterError`` like a failed
+(mixin.py:60-84)        compilation is there
+``on_device``           ``_device_fields``: device mirrors with the host's
+(mixin.py:125-160):     strides, allocated once per data set; per run H2D of
+cudaMalloc + H2D of     the fields the stencil READS and D2H of the fields it
+all fields, D2H of      WRITES (scratch fields never cross PCIe)
+all fields, every run
+``kernel(&time, ptrs)`` ``sb200_<stencil>(..., dry_runs, &time, stream)`` with
+(mixin.py:162-175)      pointers to the first interior element
+=====================  =====================================================
+
+Error mapping is the reference's: library problems -> ``ParameterError`` (so
+``sbench -s`` can skip), a failing C call -> ``benchmark.ExecutionError``.
+"""
+
+import ctypes
+import time as _time
+
+import numpy as np
+
+from .... import capi
+from ....benchmark import Benchmark, ExecutionError, Parameter, ParameterError
+from ....tools import cabi, fields
+
+_vp = ctypes.c_void_p
+
+
+class StencilMixin(Benchmark):
+    # names kept from the reference mixin (mixin.py:51-58) where they still mean something
+    backend = Parameter("GPU programming model (CUDA only)", "cuda", choices=["cuda"])
+    gpu_architecture = Parameter("GPU architecture (Blackwell B200 only)", "sm_100a",
+                                 choices=["sm_100a"])
+    print_code = Parameter("print the CUDA source of the kernel", False)
+    dry_runs = Parameter("kernel dry-runs before the measurement", 0)
+    timers = Parameter("timer type", default="gpu", choices=["gpu", "wall"])
+    # the fast (128-bit) kernels need an aligned interior origin and aligned rows
+    alignment = Parameter("data alignment in bytes", 128)
+    # new
+    device = Parameter("CUDA device ordinal", 0)
+    pinned = Parameter("allocate host fields in page-locked memory", True)
+    seed = Parameter("seed of the random input fields (negative: non-deterministic)", 42)
+
+    #: role of each field: "in" (H2D every run), "out" (D2H every run),
+    #: "inout" (both), "scratch" (device only)
+    field_roles = {}
+    #: CUDA source shown by --print-code
+    kernel_source = None
+
+    def setup(self):
+        if tuple(self.layout) != (2, 1, 0):
+            raise ParameterError(
+                f"layout {tuple(self.layout)} is not supported by the B200 kernels "
+                "(i must be the unit-stride axis: layout (2, 1, 0))"
+            )
+        try:
+            self._dtype_code = capi.dtype_code(self.dtype)
+        except (ValueError, TypeError) as error:
+            raise ParameterError(str(error)) from error
+        try:
+            self._lib = capi.library()
+        except cabi.CompilationError as error:
+            raise ParameterError(*error.args) from error
+        if self.pinned:
+            try:
+                capi.require_device()
+                self._lib.sb200_set_device(self.device)
+            except cabi.ExecutionError as error:
+                raise ParameterError(*error.args) from error
+        self._field_counter = 0
+        self._device = {}
+
+        super().setup()
+
+        if self.print_code and self.kernel_source:
+            print((capi.ROOT / "csrc" / self.kernel_source).read_text())
+
+    # ---- host fields -------------------------------------------------------
+    def alloc_field(self, domain_with_halo, layout, index_to_align):
+        return fields.alloc_array(
+            domain_with_halo,
+            self.dtype,
+            layout,
+            self.alignment,
+            index_to_align=index_to_align,
+            alloc=capi.pinned_alloc if self.pinned else None,
+        )
+
+    def random_field(self):
+        """U[0,1) over the whole padded field (base.py:106-109), reproducible per seed."""
+        data = self.empty_field()
+        seed = None if self.seed < 0 else [self.seed, self._field_counter]
+        self._field_counter += 1
+        rng = np.random.default_rng(seed)
+        # plane by plane: keeps the temporary small for multi-GB fields
+        for k in range(data.shape[2]):
+            data[:, :, k] = rng.random(data.shape[:2], dtype=np.float64).astype(data.dtype)
+        return data
+
+    def data(self, index=None):
+        """Host fields (namedtuple in ``args`` order) of a data set (default: the next one)."""
+        if index is None:
+            index = self._run % self.data_sets
+        return self._data[index]
+
+    # ---- device mirrors ------------------------------------------------------
+    def _device_fields(self, data):
+        """Device mirrors of one data set: dict name -> (DeviceBuffer, pointer to element 0)."""
+        key = id(data)
+        if key in self._device:
+            return self._device[key]
+        capi.require_device()
+        self._lib.sb200_set_device(self.device)
+        mirrors = {}
+        align = max(self.alignment, 256)
+        for name, host in zip(self.args, data):
+            nbytes = fields.nbytes(host)
+            buffer = capi.DeviceBuffer(nbytes + align)
+            # keep the host's alignment of the first interior element
+            interior = sum(s * h for s, h in zip(host.strides, self.halo))
+            first = buffer.ptr + (-(buffer.ptr + interior) % align)
+            mirrors[name] = (buffer, first)
+            if self.field_roles.get(name, "inout") == "out":
+                # written fields: halo and padding are mirrored once so D2H keeps them
+                capi.memcpy_h2d(first, host.ctypes.data, nbytes)
+        self._device[key] = mirrors
+        return mirrors
+
+    def interior_ptr(self, first, host):
+        return _vp(first + sum(s * h for s, h in zip(host.strides, self.halo)))
+
+    def upload(self, data, mirrors, stream=None):
+        for name, host in zip(self.args, data):
+            if self.field_roles.get(name, "inout") in ("in", "inout"):
+                capi.memcpy_h2d(mirrors[name][1], host.ctypes.data, fields.nbytes(host), stream,
+                                sync=False)
+        capi.synchronize(stream)
+
+    def download(self, data, mirrors, stream=None):
+        for name, host in zip(self.args, data):
+            if self.field_roles.get(name, "inout") in ("out", "inout"):
+                capi.memcpy_d2h(host.ctypes.data, mirrors[name][1], fields.nbytes(host), stream,
+                                sync=False)
+        capi.synchronize(stream)
+
+    # ---- the run protocol -------------------------------------------------------
+    def launch(self, pointers, dry_runs, time_ptr, stream):
+        """Call the stencil's C entry point; ``pointers`` maps field name -> interior void*."""
+        raise NotImplementedError
+
+    @property
+    def algorithmic_bytes(self):
+        """Minimum HBM traffic of one sweep; defaults to the sbench figure."""
+        return int(self.data_size)
+
+    def run_stencil(self, data):
+        try:
+            mirrors = self._device_fields(data)
+            t0 = _time.perf_counter()
+            self.upload(data, mirrors)
+            t1 = _time.perf_counter()
+            pointers = {
+                name: self.interior_ptr(mirrors[name][1], host)
+                for name, host in zip(self.args, data)
+            }
+            elapsed = ctypes.c_double()
+            if self.timers == "gpu":
+                self.launch(pointers, self.dry_runs, ctypes.byref(elapsed), None)
+            else:
+                if self.dry_runs:
+                    self.launch(pointers, self.dry_runs - 1, None, None)
+                capi.synchronize()
+                start = _time.perf_counter()
+                self.launch(pointers, 0, None, None)
+                capi.synchronize()
+                elapsed.value = _time.perf_counter() - start
+            t2 = _time.perf_counter()
+            self.download(data, mirrors)
+            t3 = _time.perf_counter()
+        except cabi.ExecutionError as error:
+            raise ExecutionError(*error.args) from error
+        return {
+            "time": elapsed.value,
+            "time-h2d": t1 - t0,
+            "time-d2h": t3 - t2,
+            "bandwidth-algorithmic": self.algorithmic_bytes / elapsed.value / 1e9,
+        }
+
+    def geometry(self):
+        """(nx, ny, nz, sx, sy, sz) as the C ABI expects them (element strides)."""
+        return tuple(int(d) for d in self.domain) + tuple(int(s) for s in self.strides)

@@ -1,0 +1,167 @@
+"""Loading and calling the C-ABI library, with the reference's call convention.
+
+Mirrors ``stencil_benchmarks/tools/compilation.py`` of the reference (file kept under another name):
+
+* ``Library`` wraps a shared library the way ``GnuLibrary`` (compilation.py:89-196)
+  wraps its JIT-compiled one: every attribute is a callable around the C
+  function, the C function returns ``int`` (0 = success), a non-zero return
+  raises ``ExecutionError(captured stderr)``, stderr output on success becomes a
+  Python warning and the captured stdout is the return value (that is how
+  STREAM hands back its table, stream/cuda_hip.py:121-144).
+* stdout/stderr are captured at file-descriptor level (compilation.py:54-86) so
+  output written by C code is seen.
+* ``dtype_cname`` / ``data_ptr`` (compilation.py:254-282) keep their meaning.
+
+Unlike ``GnuLibrary`` the library is pre-built in-tree by ``__graft_entry__.build()``
+(``nvcc -gencode arch=compute_100a,code=sm_100a``); ``compile_library`` offers the
+reference-style "compile this source now" path for out-of-tree use.
+"""
+
+import contextlib
+import ctypes
+import io
+import os
+import pathlib
+import subprocess
+import tempfile
+import warnings
+from typing import Iterator, List, Optional, TextIO, Tuple, Union
+
+import numpy as np
+
+
+class CompilationError(RuntimeError):
+    pass
+
+
+class ExecutionError(RuntimeError):
+    pass
+
+
+@contextlib.contextmanager
+def _redirect_fd(fileno: int, target: TextIO) -> Iterator[None]:
+    saved = os.dup(fileno)
+    try:
+        with tempfile.TemporaryFile() as capture:
+            os.dup2(capture.fileno(), fileno)
+            try:
+                yield
+            finally:
+                os.dup2(saved, fileno)
+                capture.seek(0)
+                target.write(capture.read().decode(errors="replace"))
+    finally:
+        os.close(saved)
+
+
+@contextlib.contextmanager
+def capture_output(stdout: TextIO, stderr: TextIO) -> Iterator[None]:
+    """Capture what C code writes to file descriptors 1 and 2."""
+    with _redirect_fd(1, stdout), _redirect_fd(2, stderr):
+        yield
+
+
+class Library:
+    """ctypes library whose functions follow the int-return / stderr convention."""
+
+    def __init__(self, path: Union[str, os.PathLike]):
+        self.path = pathlib.Path(path)
+        if not self.path.exists():
+            raise CompilationError(
+                f"{self.path} does not exist: build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a)"
+            )
+        self._library = ctypes.CDLL(str(self.path))
+
+    @property
+    def raw(self) -> ctypes.CDLL:
+        """The bare ctypes handle (no output capture, no exception mapping)."""
+        return self._library
+
+    def __getattr__(self, attr: str):
+        func = getattr(self._library, attr)
+
+        def wrapper(*args, argtypes=None):
+            if argtypes is not None:
+                func.argtypes = argtypes
+            stdout = io.StringIO()
+            stderr = io.StringIO()
+            with capture_output(stdout, stderr):
+                result = func(*args)
+            stdout = stdout.getvalue()
+            stderr = stderr.getvalue()
+            if result != 0:
+                raise ExecutionError(stderr)
+            if stderr:
+                warnings.warn(f"unexpected output in call to {attr}(…) to stderr:\n" + stderr)
+            return stdout
+
+        wrapper.__name__ = attr
+        return wrapper
+
+
+def compile_library(
+    sources: List[Union[str, os.PathLike]],
+    output: Union[str, os.PathLike],
+    compile_command: Optional[List[str]] = None,
+) -> Library:
+    """Compile CUDA sources into a shared library with nvcc for sm_100a and load it.
+
+    The flag handling follows ``GnuLibrary`` (compilation.py:125-128): for an nvcc
+    command ``-Xcompiler -shared -Xcompiler -fPIC`` is appended.
+    """
+    if compile_command is None:
+        compile_command = [
+            "nvcc",
+            "-std=c++17",
+            "-O3",
+            "-gencode",
+            "arch=compute_100a,code=sm_100a",
+            "-lineinfo",
+        ]
+    command = list(compile_command)
+    if command[0].endswith("nvcc"):
+        command += ["-Xcompiler", "-shared", "-Xcompiler", "-fPIC"]
+    else:
+        command += ["-shared", "-fPIC"]
+    result = subprocess.run(
+        [command[0], "-o", str(output)] + [str(s) for s in sources] + command[1:],
+        capture_output=True,
+    )
+    if result.returncode != 0:
+        raise CompilationError(result.stderr.decode())
+    if result.stdout or result.stderr:
+        warnings.warn(
+            "unexpected compilation output: " + result.stdout.decode() + result.stderr.decode()
+        )
+    return Library(output)
+
+
+_C_NAMES = {"f2": "half", "f4": "float", "f8": "double"}
+
+
+def dtype_cname(dtype) -> str:
+    """C spelling of a NumPy dtype (same mapping as the reference's dtype_cname)."""
+    dt = np.dtype(dtype)
+    key = f"{dt.kind}{dt.itemsize}"
+    if key in _C_NAMES:
+        return _C_NAMES[key]
+    if dt.kind in "iu":
+        return f"std::{'u' if dt.kind == 'u' else ''}int{8 * dt.itemsize}_t"
+    raise NotImplementedError(f"Conversion of type {dt} is not supported")
+
+
+def data_ptr(array: np.ndarray, offset: Union[int, Tuple[int, ...], None] = None) -> ctypes.c_void_p:
+    """Address of ``array[offset]`` as a ``void*``.
+
+    ``offset`` is a flat element count or an index tuple (the stencils pass the
+    halo, so the C side sees the first interior element -- the reference's
+    convention, compilation.py:273-282).
+    """
+    address = array.ctypes.data
+    if isinstance(offset, int):
+        address += offset * array.itemsize
+    elif offset is not None:
+        address += sum(int(s) * int(o) for s, o in zip(array.strides, offset))
+    return ctypes.c_void_p(address)
