@@ -8,7 +8,13 @@
 //   flx = lap[i+1] - lap;  flx = flx*(inp[i+1]-inp) > 0 ? 0 : flx      (fly alike in j)
 //   out = inp - coeff*(flx - flx[i-1] + fly - fly[j-1])
 //
-// Kernel "jmarch": a thread owns VEC consecutive i (one 128-bit vector: 2
+// Two kernels share the per-thread arithmetic below:
+//   * "tma"    (fast path, 16-byte aligned fields): inp halo tiles and coeff tiles are staged
+//              in shared memory by TMA (cp.async.bulk.tensor) through an mbarrier ring fed by a
+//              producer warp; four consumer warps march over j reading the tiles with LDS.128.
+//   * "jmarch" (any alignment, tiny domains): the same march with direct global loads.
+//
+// Per-thread scheme: a thread owns VEC consecutive i (one 128-bit vector: 2
 // doubles / 4 floats) and marches over JT rows of j.  Per row it loads the
 // VEC+4 wide inp strip [i0-2, i0+VEC+2) as aligned vectors, the coeff vector,
 // and keeps in registers the rolling state that the oracle holds in whole
@@ -19,7 +25,10 @@
 // on-the-fly form needs ~46 and would be FP64-bound on B200).  No shared
 // memory, no barriers.  HBM traffic is the algorithmic minimum: inp halo
 // columns/rows are L1/L2 hits on lines a neighbouring thread or block fetched.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace sb200 {
 namespace {
@@ -154,14 +163,255 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---------------------------------------------------------------------------------
+// TMA kernel
+// ---------------------------------------------------------------------------------
+// CTA = 4 consumer warps + 1 producer warp.  Tile: 128 threads x 16 bytes = 2 KB of i
+// (256 doubles / 512 floats), marched over `jt` rows of one k level.  Per pipeline
+// stage the producer issues three TMA boxes of R rows each (8-byte elements):
+//   A: [i_t - 16 B, +2048 B)   inp, main part        R x 2048 B
+//   B: [i_t + 2032 B, +32 B)   inp, right halo       R x   32 B   (TMA boxes are <= 256 elements)
+//   C: coeff tile                                     R x 2048 B
+// so row q of inp is the byte range [-16, 2064) around the tile = 130 16-byte vectors;
+// thread t reads vectors t, t+1, t+2 (its own values and the two i-halo values on each
+// side).  inp row q completes output row q-2, whose coeff row travels in the same stage.
+namespace tmacfg {
+constexpr int kConsumers = 128;
+constexpr int kThreads = kConsumers + 32;
+constexpr int kRowBytes = 2048;
+constexpr int kHaloBytes = 32;
+__host__ __device__ constexpr int stage_bytes(int rows) { return rows * (2 * kRowBytes + kHaloBytes); }
+__host__ __device__ constexpr int smem_bytes(int rows, int stages) { return stages * stage_bytes(rows) + 2 * stages * 8; }
+}  // namespace tmacfg
+
+template <class T, int VEC>
+__device__ __forceinline__ void read_strip(const unsigned char* a_row, const unsigned char* b_row,
+                                           int t, Strip<T, VEC>& s) {
+  auto vec = [&](int v) -> const unsigned char* {
+    return v < tmacfg::kConsumers ? a_row + 16 * v : b_row + 16 * (v - tmacfg::kConsumers);
+  };
+  if constexpr (sizeof(T) == 8) {
+    const double2 v0 = *reinterpret_cast<const double2*>(vec(t));
+    const double2 v1 = *reinterpret_cast<const double2*>(vec(t + 1));
+    const double2 v2 = *reinterpret_cast<const double2*>(vec(t + 2));
+    s.v[0] = v0.x; s.v[1] = v0.y; s.v[2] = v1.x; s.v[3] = v1.y; s.v[4] = v2.x; s.v[5] = v2.y;
+  } else {
+    const float4 v0 = *reinterpret_cast<const float4*>(vec(t));
+    const float4 v1 = *reinterpret_cast<const float4*>(vec(t + 1));
+    const float4 v2 = *reinterpret_cast<const float4*>(vec(t + 2));
+    s.v[0] = v0.z; s.v[1] = v0.w;
+    s.v[2] = v1.x; s.v[3] = v1.y; s.v[4] = v1.z; s.v[5] = v1.w;
+    s.v[6] = v2.x; s.v[7] = v2.y;
+  }
+}
+
+template <class T, int R, int S>
+__global__ void __launch_bounds__(tmacfg::kThreads, 4)
+    hdiff_tma_kernel(const __grid_constant__ CUtensorMap map_inp,
+                     const __grid_constant__ CUtensorMap map_halo,
+                     const __grid_constant__ CUtensorMap map_coeff, T* __restrict__ out, int nx,
+                     int ny, int jt, int64_t sy, int64_t sz) {
+  constexpr int VEC = VecN<T>::value;
+  constexpr int TW = tmacfg::kConsumers * VEC;
+  constexpr int STAGE = tmacfg::stage_bytes(R);
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE);
+  uint64_t* empty = full + S;
+
+  const int it = blockIdx.x * TW;  // first i of the tile
+  const int jb = blockIdx.y * jt;
+  const int je = min(jb + jt, ny);
+  const int k = blockIdx.z;
+  const int nstages = (je - jb + 4 + R - 1) / R;  // rows jb-2 .. je+1
+  const int warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], tmacfg::kConsumers / 32);
+    }
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == tmacfg::kConsumers / 32) {
+    // ===== producer warp: one lane drives the TMA ring =====
+    if ((threadIdx.x & 31) == 0) {
+      tma::prefetch_tensormap(&map_inp);
+      tma::prefetch_tensormap(&map_halo);
+      tma::prefetch_tensormap(&map_coeff);
+      const int c0 = it / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
+      for (int n = 0; n < nstages; ++n) {
+        const int slot = n % S;
+        if (n >= S) tma::mbar_wait(&empty[slot], ((n / S) - 1) & 1);
+        unsigned char* stage = smem + slot * STAGE;
+        tma::mbar_arrive_expect_tx(&full[slot], STAGE);
+        // tensor origins: inp at (i = -16 B, j = -2), coeff at (i = 0, j = 0)
+        tma::load_3d(stage, &map_inp, c0, jb + n * R, k, &full[slot]);
+        tma::load_3d(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, jb + n * R, k, &full[slot]);
+        tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const int t = threadIdx.x;
+  const int i0 = it + t * VEC;
+  const bool active = i0 < nx;
+  const bool whole = i0 + VEC <= nx;
+  T* __restrict__ op = out + int64_t(k) * sz + i0;
+
+  Strip<T, VEC> rc, rn, rnn;
+  T lc[VEC + 2], ln[VEC + 2], fym[VEC];
+#pragma unroll
+  for (int m = 0; m < VEC + 2; ++m) lc[m] = ln[m] = T(0);
+#pragma unroll
+  for (int n = 0; n < VEC; ++n) fym[n] = T(0);
+#pragma unroll
+  for (int n = 0; n < VEC + 4; ++n) rc.v[n] = rn.v[n] = T(0);
+
+  for (int n = 0; n < nstages; ++n) {
+    const int slot = n % S;
+    tma::mbar_wait(&full[slot], (n / S) & 1);
+    const unsigned char* stage = smem + slot * STAGE;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int j = jb + n * R + r - 4;  // output row completed by inp row j + 2
+      read_strip<T, VEC>(stage + r * tmacfg::kRowBytes,
+                         stage + 2 * R * tmacfg::kRowBytes + r * tmacfg::kHaloBytes, t, rnn);
+      T cf[VEC];
+      {
+        const unsigned char* c_row = stage + R * tmacfg::kRowBytes + r * tmacfg::kRowBytes + 16 * t;
+        if constexpr (sizeof(T) == 8) {
+          const double2 c = *reinterpret_cast<const double2*>(c_row);
+          cf[0] = c.x; cf[1] = c.y;
+        } else {
+          const float4 c = *reinterpret_cast<const float4*>(c_row);
+          cf[0] = c.x; cf[1] = c.y; cf[2] = c.z; cf[3] = c.w;
+        }
+      }
+      // rows so far: rc = row j, rn = row j+1, rnn = row j+2; lc = lap(j), fym = fly(j-1).
+      // The first four rows of a segment (n == 0) only fill this state; their results
+      // are computed from zero-initialised registers and never stored (j < jb).
+      laplacian<T, VEC>(rc, rn, rnn, ln);  // lap(j+1)
+      T flx[VEC + 1];
+#pragma unroll
+      for (int m = 0; m < VEC + 1; ++m)
+        flx[m] = limited(lc[m + 1] - lc[m], rc.v[m + 2] - rc.v[m + 1]);
+      T res[VEC];
+#pragma unroll
+      for (int m = 0; m < VEC; ++m) {
+        const T fy = limited(ln[m + 1] - lc[m + 1], rn.v[m + 2] - rc.v[m + 2]);
+        res[m] = rc.v[m + 2] - cf[m] * (flx[m + 1] - flx[m] + fy - fym[m]);
+        fym[m] = fy;
+      }
+      if (j >= jb && j < je && active) {
+        if (whole) {
+          store_vec<VEC, Cache::Streaming>(op + int64_t(j) * sy, res);
+        } else {
+#pragma unroll
+          for (int m = 0; m < VEC; ++m)
+            if (i0 + m < nx) op[int64_t(j) * sy + m] = res[m];
+        }
+      }
+      rc = rn;
+      rn = rnn;
+#pragma unroll
+      for (int m = 0; m < VEC + 2; ++m) lc[m] = ln[m];
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tma::mbar_arrive(&empty[slot]);
+  }
+}
+
+// SB200_HDIFF_CFG="variant,jt": variant 0 = auto, 1 = jmarch, 2 = tma; jt = rows per CTA (0 = auto)
+struct HdiffConfig {
+  int variant = 0;
+  int jt = 0;
+};
+
+inline HdiffConfig hdiff_config() {
+  HdiffConfig cfg;
+  if (const char* env = std::getenv("SB200_HDIFF_CFG")) std::sscanf(env, "%d,%d", &cfg.variant, &cfg.jt);
+  return cfg;
+}
+
+template <class T>
+int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
+                     int64_t sy, int64_t sz, int jt_request, int dry_runs, double* time,
+                     cudaStream_t stream, bool* used) {
+  constexpr int R = 4, S = 3;
+  constexpr int VEC = VecN<T>::value;
+  constexpr int TW = tmacfg::kConsumers * VEC;
+  constexpr int E = 8 / int(sizeof(T));  // data elements per 8-byte TMA element
+  *used = false;
+  // inp tensor: origin 16 bytes left of i = 0 and two rows below j = 0; extent covers
+  // i in [-16 B, nx + 2), j in [-2, ny + 2)
+  const T* inp_origin = inp - 16 / int(sizeof(T)) - 2 * sy;
+  const uint64_t inp_d0 = uint64_t(ceil_div(16 + (nx + 2) * int64_t(sizeof(T)), 8));
+  if (sizeof(T) == 4) {
+    // float32: the origin lies 2 elements outside a halo of width 2 and an odd nx rounds the
+    // extent up by one element; only take the TMA path if that memory belongs to the allocation
+    const T* last = inp_origin + (nz - 1) * sz + (ny + 3) * sy + inp_d0 * E;
+    if (!tma::range_is_allocated(inp_origin, last)) return 0;
+  }
+  CUtensorMap map_inp, map_coeff;
+  if (!tma::encode_3d_u64(&map_inp, inp_origin, inp_d0, uint64_t(ny + 4), uint64_t(nz),
+                          uint64_t(sy) * sizeof(T), uint64_t(sz) * sizeof(T), 256, R, 1))
+    return 0;
+  if (!tma::encode_3d_u64(&map_coeff, coeff, uint64_t(ceil_div(nx, E)), uint64_t(ny), uint64_t(nz),
+                          uint64_t(sy) * sizeof(T), uint64_t(sz) * sizeof(T), 256, R, 1))
+    return 0;
+  // the right-halo box (4 x 8 bytes per row) needs its own descriptor: the box shape is part of it
+  CUtensorMap map_halo;
+  if (!tma::encode_3d_u64(&map_halo, inp_origin, inp_d0, uint64_t(ny + 4), uint64_t(nz),
+                          uint64_t(sy) * sizeof(T), uint64_t(sz) * sizeof(T), 4, R, 1))
+    return 0;
+
+  const int64_t xtiles = ceil_div(nx, TW);
+  int jt = jt_request;
+  if (jt <= 0) {
+    // enough CTAs for ~8 per SM, but long marches where the domain allows it
+    const int64_t target = 148 * 8;
+    int64_t segments = ceil_div(target, xtiles * nz);
+    jt = int(std::min<int64_t>(128, std::max<int64_t>(16, ceil_div(ny, segments))));
+  }
+  jt = int(ceil_div(jt, R)) * R;
+  const dim3 grid(unsigned(xtiles), unsigned(ceil_div(ny, jt)), unsigned(nz));
+  if (grid.y > 65535u || grid.z > 65535u) return fail("sb200_hdiff: domain too large for the launch grid");
+  constexpr int smem = tmacfg::smem_bytes(R, S);
+  static bool configured = false;
+  if (!configured) {
+    SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  *used = true;
+  auto launch = [&] {
+    hdiff_tma_kernel<T, R, S><<<grid, tmacfg::kThreads, smem, stream>>>(map_inp, map_halo, map_coeff, out, int(nx),
+                                                                       int(ny), jt, sy, sz);
+    count_launch();
+  };
+  return timed(launch, dry_runs, time, stream);
+}
+
 template <class T>
 int launch_hdiff(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
                  int64_t sy, int64_t sz, int dry_runs, double* time, cudaStream_t stream) {
   constexpr int V = VecN<T>::value;
   constexpr int JT = 64;
-  // vector path: 16-byte aligned interior origin and strides that keep every row aligned
+  const HdiffConfig cfg = hdiff_config();
+  // vector paths: 16-byte aligned interior origin and strides that keep every row aligned
   const bool vector_ok = aligned_to(inp, 16) && aligned_to(coeff, 16) && aligned_to(out, 16) &&
                          sy % V == 0 && sz % V == 0;
+  // TMA path: worth it once a 2 KB tile is at least half full
+  if (vector_ok && cfg.variant != 1 && (cfg.variant == 2 || nx * int64_t(sizeof(T)) >= 1024)) {
+    bool used = false;
+    const int rc = launch_hdiff_tma<T>(inp, coeff, out, nx, ny, nz, sy, sz, cfg.jt, dry_runs, time,
+                                       stream, &used);
+    if (used || rc != 0) return rc;
+  }
   const int vec = vector_ok ? V : 1;
   const int64_t nvec = ceil_div(nx, vec);
   int bx = 128;

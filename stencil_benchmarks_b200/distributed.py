@@ -1,0 +1,147 @@
+"""Multi-GPU plumbing: J partition of the IJ plane and the width-h halo exchange.
+
+New functionality with respect to the reference, which is single-GPU
+(SURVEY.md §2, §8e).  One process per GPU (``torch.distributed``: NCCL on GPUs,
+gloo in the CPU tests); the global domain is split along j into contiguous
+slabs so rows stay i-contiguous.  Per sweep each rank sends its first / last
+``width`` interior rows to the lower / upper neighbour and receives their
+counterparts into its own halo rows.  The outermost halos of the global domain
+keep the values the host provided (the reference has no boundary condition), so
+results are bit-identical to a single-GPU run of the global domain.
+
+STREAM, the basic copy and vertical advection need no exchange: vadv reads
+wcon(i+1, j) only, and i is not partitioned.
+
+The exchange is written against three injected callables (make_buffer, pack,
+unpack) so the same neighbour / row arithmetic runs with CUDA kernels + NCCL in
+production (``cuda_halo_exchange``) and with NumPy + gloo in the CPU tests.
+"""
+
+from typing import Callable, List, Optional, Tuple
+
+
+def split_rows(ny_global: int, world_size: int) -> List[Tuple[int, int]]:
+    """(first row, row count) of every rank; the remainder goes to the first ranks."""
+    if world_size < 1 or ny_global < world_size:
+        raise ValueError(f"cannot split {ny_global} rows over {world_size} ranks")
+    base, extra = divmod(ny_global, world_size)
+    rows, start = [], 0
+    for rank in range(world_size):
+        count = base + (1 if rank < extra else 0)
+        rows.append((start, count))
+        start += count
+    return rows
+
+
+def neighbours(rank: int, world_size: int) -> Tuple[Optional[int], Optional[int]]:
+    """(lower, upper) neighbour in j; None at the ends of the global domain (no periodicity)."""
+    lower = rank - 1 if rank > 0 else None
+    upper = rank + 1 if rank < world_size - 1 else None
+    return lower, upper
+
+
+def interior_and_boundary_rows(ny: int, reach: int, has_lower: bool, has_upper: bool):
+    """Rows that can be computed before the halos arrive, and the strips that cannot.
+
+    A stencil reaching ``reach`` rows in j (2 for horizontal diffusion) can update
+    rows [lo, hi) without the neighbours' data; the strips [0, lo) and [hi, ny)
+    wait for the exchange.  Returns ((lo, hi), [(start, stop), ...]).
+    """
+    lo = min(reach, ny) if has_lower else 0
+    hi = max(ny - reach, lo) if has_upper else ny
+    strips = []
+    if lo > 0:
+        strips.append((0, lo))
+    if hi < ny:
+        strips.append((hi, ny))
+    return (lo, hi), strips
+
+
+class HaloExchange:
+    """Width-``width`` halo exchange of one field along j between neighbouring ranks.
+
+    make_buffer(nrows) -> a buffer object accepted by ``dist.isend`` / ``dist.irecv``
+    pack(field, j0, nrows, buffer)    copy rows [j0, j0+nrows) of every level into buffer
+    unpack(field, j0, nrows, buffer)  the inverse
+    Row indices are relative to the first interior row (negative = lower halo).
+    """
+
+    def __init__(self, dist, rank: int, world_size: int, ny: int, width: int,
+                 make_buffer: Callable, pack: Callable, unpack: Callable, group=None):
+        if width > ny:
+            raise ValueError("halo wider than the local slab")
+        self.dist = dist
+        self.rank, self.world_size = rank, world_size
+        self.ny, self.width = ny, width
+        self.pack, self.unpack = pack, unpack
+        self.group = group
+        self.lower, self.upper = neighbours(rank, world_size)
+        self.send_lower = make_buffer(width) if self.lower is not None else None
+        self.recv_lower = make_buffer(width) if self.lower is not None else None
+        self.send_upper = make_buffer(width) if self.upper is not None else None
+        self.recv_upper = make_buffer(width) if self.upper is not None else None
+
+    def start(self, field):
+        """Pack the edge rows and post the sends / receives; returns the pending requests."""
+        ops = []
+        P2POp = self.dist.P2POp
+        if self.lower is not None:
+            self.pack(field, 0, self.width, self.send_lower)
+            ops.append(P2POp(self.dist.isend, self.send_lower, self.lower, self.group))
+            ops.append(P2POp(self.dist.irecv, self.recv_lower, self.lower, self.group))
+        if self.upper is not None:
+            self.pack(field, self.ny - self.width, self.width, self.send_upper)
+            ops.append(P2POp(self.dist.isend, self.send_upper, self.upper, self.group))
+            ops.append(P2POp(self.dist.irecv, self.recv_upper, self.upper, self.group))
+        return self.dist.batch_isend_irecv(ops) if ops else []
+
+    def finish(self, field, requests):
+        """Wait for the messages and write them into the halo rows."""
+        for request in requests:
+            request.wait()
+        if self.lower is not None:
+            self.unpack(field, -self.width, self.width, self.recv_lower)
+        if self.upper is not None:
+            self.unpack(field, self.ny, self.width, self.recv_upper)
+
+    @property
+    def bytes_per_exchange(self):
+        """Bytes this rank sends per sweep."""
+        total = 0
+        for buffer in (self.send_lower, self.send_upper):
+            if buffer is not None:
+                total += buffer.numel() * buffer.element_size()
+        return total
+
+
+def cuda_halo_exchange(rank, world_size, dtype, nx, ny, nz, hx, sy, sz, width, group=None):
+    """HaloExchange whose pack / unpack are the sb200 CUDA kernels and whose buffers are
+    torch CUDA tensors (NCCL send/recv over NVLink).  ``field`` is the device address of
+    the first interior element (an int)."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+
+    lib = capi.library()
+    code = capi.dtype_code(dtype)
+    torch_dtype = {"float64": torch.float64, "float32": torch.float32}[str(dtype)]
+    row_len = nx + 2 * hx
+
+    def make_buffer(nrows):
+        return torch.empty(row_len * nrows * nz, dtype=torch_dtype, device="cuda")
+
+    def stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def pack(field, j0, nrows, buffer):
+        lib.raw.sb200_pack_rows(code, ctypes.c_void_p(field), ctypes.c_void_p(buffer.data_ptr()),
+                                nx, nz, hx, sy, sz, j0, nrows, stream())
+
+    def unpack(field, j0, nrows, buffer):
+        lib.raw.sb200_unpack_rows(code, ctypes.c_void_p(field), ctypes.c_void_p(buffer.data_ptr()),
+                                  nx, nz, hx, sy, sz, j0, nrows, stream())
+
+    return HaloExchange(dist, rank, world_size, ny, width, make_buffer, pack, unpack, group)
