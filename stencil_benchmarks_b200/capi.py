@@ -11,6 +11,7 @@ raises, and every benchmark that needs it fails with that error.
 
 import ctypes
 import functools
+import os
 import pathlib
 import re
 import weakref
@@ -103,7 +104,18 @@ def dtype_code(dtype) -> int:
     raise ValueError(f"unsupported dtype {dtype}: the B200 kernels exist for float32 and float64")
 
 
+def driver_present() -> bool:
+    """True if the NVIDIA kernel driver exposes its device nodes.
+
+    Checked before any CUDA runtime call: on a machine without the driver the
+    runtime can block for minutes instead of reporting "no device".
+    """
+    return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/dxg")
+
+
 def device_count() -> int:
+    if not driver_present():
+        return 0
     count = _i(0)
     library().sb200_device_count(ctypes.byref(count))
     return count.value

@@ -54,6 +54,26 @@ inline bool range_is_allocated(const void* begin, const void* end) {
   return reinterpret_cast<CUdeviceptr>(end) <= base + size;
 }
 
+// 3-D tiled tensor map, no swizzle, zero OOB fill; dims in elements, strides in bytes.
+inline bool encode_3d(CUtensorMap* map, CUtensorMapDataType type, const void* base, uint64_t d0,
+                      uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                      uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  const cuuint32_t box[3] = {b0, b1, b2};
+  const cuuint32_t elem[3] = {1, 1, 1};
+  return fn(map, type, 3, const_cast<void*>(base), dims, strides, box, elem,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <class T>
+constexpr CUtensorMapDataType tensor_type() {
+  return sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
 // 3-D tiled tensor map over 8-byte elements (used for float64 data and for
 // pairs of float32): dims/strides in elements/bytes, no swizzle, zero OOB fill.
 inline bool encode_3d_u64(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,

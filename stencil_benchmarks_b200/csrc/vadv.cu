@@ -7,6 +7,10 @@
 // reciprocal-then-multiply on interior levels and true division on the first
 // and last level.
 //
+// Variant ONCHIP (fast path, see the block comment above vadv_onchip_kernel): the eliminated
+// coefficients never leave the SM -- c lives in tensor memory (TMEM), the folded right-hand side
+// in shared memory -- so HBM traffic is the algorithmic minimum of 5 reads + 1 write.
+//
 // Variant GLOBAL ("classic" data flow): one thread per (i, j) column,
 // consecutive lanes on consecutive i so every level is one coalesced row
 // segment per field; forward sweep k = 0..nz-1 keeps wcon / ustage of the
@@ -14,7 +18,10 @@
 // eliminated c and d to the ccol / dcol scratch fields; the backward sweep
 // reads them back.  HBM traffic: 5 reads + 2 writes forward, 3 reads + 1 write
 // backward.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace sb200 {
 namespace {
@@ -111,11 +118,474 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ---------------------------------------------------------------------------------
+// ONCHIP variant
+// ---------------------------------------------------------------------------------
+// Persistent CTAs (one per SM): 4 compute warps + 1 TMA producer warp.  A batch is 128
+// consecutive-i columns of one j row; thread t owns column i_t + t for all levels.
+//
+//  * Input levels arrive through a TMA ring (boxes of 128 columns x KD levels for ustage,
+//    upos, utens, utensstage; 128 + 16 bytes wide for wcon so that wcon(i+1) of the last
+//    column is in the tile -- TMA needs 16-byte aligned box origins, so the i+1 neighbour
+//    cannot be a second, shifted box; the j+1 neighbour of the v component can), so the
+//    k-sequential compute never waits on a global load it issued itself and ~60 KB per SM
+//    are in flight.
+//  * The Thomas coefficients of a column are private to its thread: c[k] is parked in TMEM
+//    (tcgen05.st/ld, lane = thread, two 32-bit columns per double), and the right-hand side in
+//    shared memory, already folded for the backward sweep:
+//        e[k] = d[k] - pos[k] - c[k]*pos[k+1]   =>   z[k] = x[k] - pos[k] = e[k] - c[k]*z[k+1],
+//        utensstage[k] = dtr * z[k]
+//    so the backward sweep reads nothing from HBM.
+//  * The backward sweep of batch n runs in lock-step with the forward sweep of batch n+1:
+//    at step s the thread consumes slot p of the old column (level nz-1-s) and then stores the
+//    new column's level s-1 into the same slot.  One set of nz-1 slots per thread suffices and
+//    the two dependency chains (forward with its division, backward FMA) overlap.
+// HBM traffic = 5 reads + 1 write per point; storage limits: (nz-1) * 128 * sizeof(T) bytes of
+// shared memory next to the ring, (nz-1) * sizeof(T)/4 <= 512 TMEM columns.
+namespace vcfg {
+constexpr int kCols = 128;
+constexpr int kThreads = kCols + 32;
+constexpr int kTmemCols = 512;
+// ring stage = 4 tiles of KD x 128 values + 2 wcon tiles of KD x (128 + 16 B) values, the
+// latter padded to 128 bytes so every TMA destination stays 128-byte aligned
+template <class T>
+__host__ __device__ constexpr int wcon_width() { return kCols + 16 / int(sizeof(T)); }
+template <class T>
+__host__ __device__ constexpr int tile_bytes(int kd) { return kd * kCols * int(sizeof(T)); }
+template <class T>
+__host__ __device__ constexpr int wcon_bytes(int kd) { return kd * wcon_width<T>() * int(sizeof(T)); }
+template <class T>
+__host__ __device__ constexpr int wcon_tile_bytes(int kd) { return (wcon_bytes<T>(kd) + 127) / 128 * 128; }
+template <class T>
+__host__ __device__ constexpr int stage_bytes(int kd) { return 4 * tile_bytes<T>(kd) + 2 * wcon_tile_bytes<T>(kd); }
+}  // namespace vcfg
+
+__device__ __forceinline__ void tmem_store(uint32_t taddr, double v) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr),
+               "r"((uint32_t)(bits & 0xffffffffull)), "r"((uint32_t)(bits >> 32)));
+}
+__device__ __forceinline__ void tmem_store(uint32_t taddr, float v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)));
+}
+__device__ __forceinline__ void tmem_load(uint32_t taddr, double& v) {
+  uint32_t lo, hi;
+  // volatile without a memory clobber: TMEM accesses keep their mutual order, ordinary loads,
+  // stores and arithmetic are free to move around them.  The wait ties the registers.
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(lo), "+r"(hi));
+  v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+__device__ __forceinline__ void tmem_load(uint32_t taddr, float& v) {
+  uint32_t bits;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(bits) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(bits));
+  v = __uint_as_float(bits);
+}
+
+// Reciprocal from the hardware seed (MUFU.RCP64H, ~2^-23) and two Newton steps: full double
+// precision up to the last ulp, no special-case branches, 5 FP64 instructions on the critical path
+// of nothing (the recurrence below is division free).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double t = fma(-x, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-x, r, 1.0);
+  return fma(r, t, r);
+}
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
+
+// Exact power-of-two renormalisation of the homogeneous triple (p, r, q) so that q is in [1, 2).
+__device__ __forceinline__ void rescale(double& p, double& r, double& q) {
+  const int ex = (__double2hiint(q) >> 20) & 0x7ff;
+  const double f = __hiloint2double((2046 - ex) << 20, 0);
+  p *= f;
+  r *= f;
+  q *= f;
+}
+__device__ __forceinline__ void rescale(float& p, float& r, float& q) {
+  const unsigned ex = (__float_as_uint(q) >> 23) & 0xffu;
+  const float f = __uint_as_float((254u - ex) << 23);
+  p *= f;
+  r *= f;
+  q *= f;
+}
+
+// Forward state of the column a thread is eliminating.  c[k] = p/q and d[k] = r/q are kept as a
+// homogeneous triple: with a, b, cc, d0 the coefficients of level k (base.py:432-445),
+//     c[k] = cc / (b - c[k-1] a)            =>  p' = cc q,  q' = b q - a p
+//     d[k] = (d0 - d[k-1] a) / (b - c[k-1] a)  =>  r' = d0 q - a r
+// so the level-to-level dependency is two FMAs instead of a division; the division needed to
+// store c[k], d[k] is off the critical path and pipelines across levels.
+template <class T>
+struct VadvForward {
+  T wsum_cur = 0, wsum_next = 0, st_prev = 0, st_cur = 0, st_next = 0;
+  T pos_cur = 0, tens_cur = 0, tss_cur = 0;
+  T p = 0, r = 0, q = 1;
+};
+
+// One lock-step iteration: level s of the new column has arrived (values v_*), level k = s-1 is
+// eliminated and stored in slot `slot`, after the old column's level nz-1-s has been
+// back-substituted from the same slot.  FIRST: s may be 0 or 1 (resolved at compile time in the
+// peeled first chunk).
+template <class T, bool FIRST>
+__device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T v_pos, T v_tens,
+                                          T v_tss, T v_wsum, T& z, uint32_t tmem_slot, T* eslot,
+                                          T* old_out, bool old_valid) {
+  using C = VadvConst<T>;
+  constexpr int TCOLS = int(sizeof(T)) / 4;
+  const T dtr_stage = C::dtr_stage, bet_m = C::bet_m, bet_p = C::bet_p;
+  f.wsum_cur = f.wsum_next;
+  f.wsum_next = v_wsum;
+  f.st_prev = f.st_cur;
+  f.st_cur = f.st_next;
+  f.st_next = v_stage;
+  if (FIRST && s == 0) {
+    f.pos_cur = v_pos; f.tens_cur = v_tens; f.tss_cur = v_tss;
+    return;
+  }
+  T pn, rn, qn;
+  if (FIRST && s == 1) {
+    // level 0 (base.py:417-429): c = cc / b, d = d0 / b
+    const T gcv = T(0.25) * f.wsum_next;
+    const T cs = gcv * bet_m;
+    const T cc = gcv * bet_p;
+    const T b = dtr_stage - cc;
+    const T correction = -cs * (f.st_next - f.st_cur);
+    const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur + correction;
+    pn = cc; rn = d0; qn = b;
+  } else {
+    const T gav = T(-0.25) * f.wsum_cur;
+    const T gcv = T(0.25) * f.wsum_next;
+    const T as = gav * bet_m;
+    const T cs = gcv * bet_m;
+    const T a = gav * bet_p;
+    const T cc = gcv * bet_p;
+    const T b = dtr_stage - a - cc;
+    const T correction = -as * (f.st_prev - f.st_cur) - cs * (f.st_next - f.st_cur);
+    const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur + correction;
+    pn = cc * f.q;
+    qn = b * f.q - a * f.p;
+    rn = d0 * f.q - a * f.r;
+  }
+  f.p = pn; f.r = rn; f.q = qn;
+  const T rq = fast_rcp(qn);
+  const T c = pn * rq;
+  const T d = rn * rq;
+  const T e = d - f.pos_cur - c * v_pos;  // folded right-hand side of level s-1
+  // backward step of the old column on the slot that is about to be overwritten
+  T c_old;
+  tmem_load(tmem_slot, c_old);
+  z = *eslot - c_old * z;
+  if (old_valid) *old_out = dtr_stage * z;
+  tmem_store(tmem_slot, c);
+  *eslot = e;
+  (void)TCOLS;
+  f.pos_cur = v_pos; f.tens_cur = v_tens; f.tss_cur = v_tss;
+}
+
+template <class T, int KD>
+__global__ void __launch_bounds__(vcfg::kThreads, 1)
+    vadv_onchip_kernel(const __grid_constant__ CUtensorMap map_stage,
+                       const __grid_constant__ CUtensorMap map_pos,
+                       const __grid_constant__ CUtensorMap map_tens,
+                       const __grid_constant__ CUtensorMap map_tensstage,
+                       const __grid_constant__ CUtensorMap map_wcon, T* __restrict__ tensstage,
+                       int nx, int ny, int nz, int64_t sy, int64_t sz, int ishift, int jshift,
+                       int stages) {
+  using C = VadvConst<T>;
+  constexpr int COLS = vcfg::kCols;
+  constexpr int TILE = vcfg::tile_bytes<T>(KD);           // one field, KD levels
+  constexpr int WB = vcfg::wcon_width<T>();                // wcon tile width in elements
+  constexpr int WTILE = vcfg::wcon_tile_bytes<T>(KD);
+  constexpr int TCOLS = int(sizeof(T)) / 4;                // TMEM columns per value
+  const int STAGE = 4 * TILE + (jshift ? 2 : 1) * WTILE;
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [ring: stages x STAGE][e store: (nz-1) x COLS][barriers][tmem base]
+  unsigned char* ring = smem;
+  T* estore = reinterpret_cast<T*>(smem + stages * STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * STAGE + size_t(nz - 1) * COLS * sizeof(T));
+  uint64_t* empty = full + stages;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(empty + stages);
+
+  const int warp = threadIdx.x >> 5;
+  const int nbx = (nx + COLS - 1) / COLS;
+  const int nbatches = nbx * ny;
+  const int nchunks = (nz + KD - 1) / KD;
+  // batches of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_batches = (nbatches - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], COLS / 32);
+    }
+    tma::fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     tma::smem_u32(tmem_base_smem)),
+                 "r"(vcfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (warp == COLS / 32) {
+    // ===== producer warp =====
+    if ((threadIdx.x & 31) == 0) {
+      tma::prefetch_tensormap(&map_stage);
+      tma::prefetch_tensormap(&map_pos);
+      tma::prefetch_tensormap(&map_tens);
+      tma::prefetch_tensormap(&map_tensstage);
+      tma::prefetch_tensormap(&map_wcon);
+      const uint32_t tx_bytes = 4 * TILE + (jshift ? 2 : 1) * vcfg::wcon_bytes<T>(KD);
+      int slot = 0, round = 0;  // ring position of the running chunk counter
+      for (int m = 0; m < my_batches; ++m) {
+        const int b = int(blockIdx.x) + m * int(gridDim.x);
+        const int j = b / nbx;
+        const int it = (b - j * nbx) * COLS;
+        for (int c = 0; c < nchunks; ++c) {
+          if (round > 0) tma::mbar_wait(&empty[slot], (round - 1) & 1);
+          unsigned char* stage = ring + slot * STAGE;
+          tma::mbar_arrive_expect_tx(&full[slot], tx_bytes);
+          const int k0 = c * KD;
+          tma::load_3d(stage + 0 * TILE, &map_stage, it, j, k0, &full[slot]);
+          tma::load_3d(stage + 1 * TILE, &map_pos, it, j, k0, &full[slot]);
+          tma::load_3d(stage + 2 * TILE, &map_tens, it, j, k0, &full[slot]);
+          tma::load_3d(stage + 3 * TILE, &map_tensstage, it, j, k0, &full[slot]);
+          tma::load_3d(stage + 4 * TILE, &map_wcon, it, j, k0, &full[slot]);
+          if (jshift) tma::load_3d(stage + 4 * TILE + WTILE, &map_wcon, it, j + 1, k0, &full[slot]);
+          if (++slot == stages) {
+            slot = 0;
+            ++round;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== compute warps =====
+    const int t = threadIdx.x;
+    const T dtr_stage = C::dtr_stage, bet_m = C::bet_m, bet_p = C::bet_p;
+    const uint32_t tmem_lane = *tmem_base_smem + (uint32_t(warp * 32) << 16);
+    T* ecol = estore + t;  // slot p at ecol[p * COLS]
+
+    VadvForward<T> f;
+    T z = 0;                // backward state of the old column: x - pos of the level above
+    T* old_base = tensstage;
+    bool old_valid = false;
+    int slot = 0, round = 0;
+    int dir = 0;  // slot direction of the NEW column: level k -> slot (dir ? nz-2-k : k)
+
+    // values of level r of the chunk in ring slot `slot`
+    auto fetch = [&](const unsigned char* stage, int r, T& v_stage, T& v_pos, T& v_tens, T& v_tss,
+                     T& v_wsum) {
+      auto tile = [&](int field) { return reinterpret_cast<const T*>(stage + field * TILE)[r * COLS + t]; };
+      v_stage = tile(0);
+      v_pos = tile(1);
+      v_tens = tile(2);
+      v_tss = tile(3);
+      // shifted + unshifted wcon, in the oracle's order: i+1 from the same (wider) tile,
+      // j+1 from the second tile
+      const T* w0 = reinterpret_cast<const T*>(stage + 4 * TILE) + r * WB + t;
+      const T* w1 = reinterpret_cast<const T*>(stage + 4 * TILE + WTILE) + r * WB + t;
+      v_wsum = (jshift ? w1[0] : w0[ishift]) + w0[0];
+    };
+    auto release = [&]() {
+      __syncwarp();
+      if ((t & 31) == 0) tma::mbar_arrive(&empty[slot]);
+      if (++slot == stages) {
+        slot = 0;
+        ++round;
+      }
+    };
+
+    for (int m = 0; m < my_batches; ++m) {
+      const int b = int(blockIdx.x) + m * int(gridDim.x);
+      const int j = b / nbx;
+      const int i = (b - j * nbx) * COLS + t;
+      const bool new_valid = i < nx;
+      T* new_base = tensstage + int64_t(j) * sy + i;
+      // slot of the new column's level s-1 / the old column's level nz-1-s at step s
+      const int p0 = dir ? nz - 1 : -1;
+      const int dp = dir ? -1 : 1;  // slot(s) = p0 + dp * s
+
+      // ---- first chunk, peeled: levels 0 and 1 are special ----
+      {
+        tma::mbar_wait(&full[slot], round & 1);
+        const unsigned char* stage = ring + slot * STAGE;
+        T v_stage[KD], v_pos[KD], v_tens[KD], v_tss[KD], v_wsum[KD];
+#pragma unroll
+        for (int r = 0; r < KD; ++r) fetch(stage, r, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r]);
+        release();
+#pragma unroll
+        for (int r = 0; r < KD; ++r) {
+          if (r < nz) {
+            const int pslot = p0 + dp * r;
+            vadv_step<T, true>(r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
+                               tmem_lane + uint32_t(pslot * TCOLS), ecol + pslot * COLS,
+                               old_base + int64_t(nz - 1 - r) * sz, old_valid);
+          }
+        }
+      }
+      // ---- full chunks ----
+      int s0 = KD;
+      for (; s0 + KD <= nz; s0 += KD) {
+        tma::mbar_wait(&full[slot], round & 1);
+        const unsigned char* stage = ring + slot * STAGE;
+        T v_stage[KD], v_pos[KD], v_tens[KD], v_tss[KD], v_wsum[KD];
+#pragma unroll
+        for (int r = 0; r < KD; ++r) fetch(stage, r, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r]);
+        release();
+        rescale(f.p, f.r, f.q);
+#pragma unroll
+        for (int r = 0; r < KD; ++r) {
+          const int s = s0 + r;
+          const int pslot = p0 + dp * s;
+          vadv_step<T, false>(s, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
+                              tmem_lane + uint32_t(pslot * TCOLS), ecol + pslot * COLS,
+                              old_base + int64_t(nz - 1 - s) * sz, old_valid);
+        }
+      }
+      // ---- last, partial chunk ----
+      if (s0 < nz) {
+        tma::mbar_wait(&full[slot], round & 1);
+        const unsigned char* stage = ring + slot * STAGE;
+        rescale(f.p, f.r, f.q);
+        for (int s = s0; s < nz; ++s) {
+          T v_stage, v_pos, v_tens, v_tss, v_wsum;
+          fetch(stage, s - s0, v_stage, v_pos, v_tens, v_tss, v_wsum);
+          const int pslot = p0 + dp * s;
+          vadv_step<T, false>(s, f, v_stage, v_pos, v_tens, v_tss, v_wsum, z,
+                              tmem_lane + uint32_t(pslot * TCOLS), ecol + pslot * COLS,
+                              old_base + int64_t(nz - 1 - s) * sz, old_valid);
+        }
+        release();
+      }
+      // ---- step nz: last level k = nz-1 of the new column (base.py:451-462) starts its
+      //      backward sweep; the old column finished at step nz-1 ----
+      {
+        const T gav = T(-0.25) * f.wsum_next;
+        const T as = gav * bet_m;
+        const T a = gav * bet_p;
+        const T bb = dtr_stage - a;
+        const T correction = -as * (f.st_cur - f.st_next);
+        const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur + correction;
+        const T x_top = (d0 * f.q - a * f.r) / (bb * f.q - a * f.p);
+        z = x_top - f.pos_cur;
+        if (new_valid) new_base[int64_t(nz - 1) * sz] = dtr_stage * z;
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      old_base = new_base;
+      old_valid = new_valid;
+      dir ^= 1;
+    }
+    // ---- drain: backward sweep of the last column ----
+    if (my_batches > 0) {
+      const int p0 = dir ? nz - 1 : -1;
+      const int dp = dir ? -1 : 1;
+      for (int s = 1; s <= nz - 1; ++s) {
+        const int pslot = p0 + dp * s;
+        T c_old;
+        tmem_load(tmem_lane + uint32_t(pslot * TCOLS), c_old);
+        z = ecol[pslot * COLS] - c_old * z;
+        if (old_valid) old_base[int64_t(nz - 1 - s) * sz] = dtr_stage * z;
+      }
+    }
+  }
+
+  // ---- teardown: the allocating warp frees TMEM after everybody is done ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_smem),
+                 "r"(vcfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// SB200_VADV_CFG="variant": 0 = auto, 1 = global, 2 = onchip (overrides the `variant` argument)
+inline int vadv_variant_override() {
+  if (const char* env = std::getenv("SB200_VADV_CFG")) return std::atoi(env);
+  return 0;
+}
+
+inline int sm_count() {
+  static int count = [] {
+    int device = 0, n = 148;
+    if (cudaGetDevice(&device) == cudaSuccess)
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n;
+  }();
+  return count;
+}
+
+template <class T>
+int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage, const T* wcon,
+                       int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz, int ishift,
+                       int jshift, int dry_runs, double* time, cudaStream_t stream, bool* used) {
+  constexpr int KD = 4;
+  constexpr int COLS = vcfg::kCols;
+  *used = false;
+  // as many ring stages as fit next to the per-column store (at least 2, at most 4)
+  const size_t stage_size = 4 * vcfg::tile_bytes<T>(KD) + (jshift ? 2 : 1) * vcfg::wcon_tile_bytes<T>(KD);
+  const size_t fixed = size_t(nz - 1) * COLS * sizeof(T) + 128;
+  if (fixed + 2 * stage_size > 227 * 1024) return 0;
+  const int stages = int(std::min<size_t>(4, (227 * 1024 - fixed) / stage_size));
+  const size_t smem = stages * stage_size + fixed;
+  if ((nz - 1) * int64_t(sizeof(T) / 4) > vcfg::kTmemCols) return 0;
+  const auto type = tma::tensor_type<T>();
+  const uint64_t s1 = uint64_t(sy) * sizeof(T), s2 = uint64_t(sz) * sizeof(T);
+  CUtensorMap m_stage, m_pos, m_tens, m_tss, m_wcon;
+  if (!tma::encode_3d(&m_stage, type, stage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
+      !tma::encode_3d(&m_pos, type, pos, nx, ny, nz, s1, s2, COLS, 1, KD) ||
+      !tma::encode_3d(&m_tens, type, tens, nx, ny, nz, s1, s2, COLS, 1, KD) ||
+      !tma::encode_3d(&m_tss, type, tensstage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
+      !tma::encode_3d(&m_wcon, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::wcon_width<T>(), 1, KD))
+    return 0;
+  static bool configured = false;
+  if (!configured) {
+    SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int64_t nbatches = ceil_div(nx, COLS) * ny;
+  const unsigned grid = unsigned(std::min<int64_t>(nbatches, sm_count()));
+  *used = true;
+  auto launch = [&] {
+    vadv_onchip_kernel<T, KD><<<grid, vcfg::kThreads, smem, stream>>>(
+        m_stage, m_pos, m_tens, m_tss, m_wcon, tensstage, int(nx), int(ny), int(nz), sy, sz, ishift, jshift,
+        stages);
+    count_launch();
+  };
+  return timed(launch, dry_runs, time, stream);
+}
+
 template <class T>
 int launch_vadv(const T* stage, const T* pos, const T* tens, T* tensstage, const T* wcon, T* ccol,
                 T* dcol, int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz, int ishift,
                 int jshift, int variant, int dry_runs, double* time, cudaStream_t stream) {
-  if (variant == SB200_VADV_ONCHIP) return fail("sb200_vadv: on-chip variant not available for this configuration");
+  if (const int forced = vadv_variant_override()) variant = forced;
+  constexpr int V = VecN<T>::value;
+  const bool aligned = aligned_to(stage, 16) && aligned_to(pos, 16) && aligned_to(tens, 16) &&
+                       aligned_to(tensstage, 16) && aligned_to(wcon, 16) && sy % V == 0 && sz % V == 0;
+  if (variant != SB200_VADV_GLOBAL) {
+    // the on-chip variant pays off once most of a 128-column batch is populated
+    const bool wanted = variant == SB200_VADV_ONCHIP || nx >= 64;
+    bool used = false;
+    if (aligned && wanted) {
+      const int rc = launch_vadv_onchip<T>(stage, pos, tens, tensstage, wcon, nx, ny, nz, sy, sz, ishift,
+                                           jshift, dry_runs, time, stream, &used);
+      if (used || rc != 0) return rc;
+    }
+    if (variant == SB200_VADV_ONCHIP)
+      return fail("sb200_vadv: on-chip variant not available for this configuration "
+                  "(needs 16-byte aligned fields and (nz-1)*128*sizeof(T) bytes of shared memory)");
+  }
   if (ccol == nullptr || dcol == nullptr) return fail("sb200_vadv: ccol/dcol scratch fields are required by the global variant");
   int bx = 64;
   while (bx > 32 && bx / 2 >= nx) bx /= 2;

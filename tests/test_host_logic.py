@@ -1,0 +1,183 @@
+"""Host side of the B200 backend without a GPU: registration names, parameter validation,
+field layout, byte accounting, C-ABI symbol table."""
+
+import ctypes
+import subprocess
+
+import numpy as np
+import pytest
+
+from stencil_benchmarks_b200 import benchmark, capi
+from stencil_benchmarks_b200 import benchmarks_collection  # noqa: F401  (registers the classes)
+from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import (
+    basic,
+    horizontal_diffusion,
+    vertical_advection,
+)
+from stencil_benchmarks_b200.benchmarks_collection.stream import b200 as stream
+from stencil_benchmarks_b200.tools import cabi, fields
+
+CPU = dict(pinned=False, verify=False)  # no device needed to construct
+
+
+def cli_path(cls):
+    """Command path stencil_benchmarks.cli derives for a class (cli.py:47-50, :230)."""
+    def kebab(name):
+        out = ""
+        for ch in name:
+            out += ("-" + ch.lower()) if ch.isupper() and out else ch.lower()
+        return out
+    return [part.replace("_", "-") for part in cls.__module__.split(".")[2:]] + [kebab(cls.__name__)]
+
+
+def test_registered_command_names():
+    names = {" ".join(cli_path(c)) for c in benchmark.REGISTRY
+             if c.__module__.startswith("stencil_benchmarks_b200.")}
+    assert names == {
+        "stencils b200 basic empty", "stencils b200 basic copy",
+        "stencils b200 basic onesided-average", "stencils b200 basic symmetric-average",
+        "stencils b200 basic laplacian", "stencils b200 horizontal-diffusion fused",
+        "stencils b200 vertical-advection thomas", "stream b200 native",
+    }
+
+
+def test_library_exports_every_declared_symbol():
+    declared = capi.declared_symbols()
+    assert set(declared) == set(capi.PROTOTYPES), "include/sbench_b200.h and capi.PROTOTYPES differ"
+    lib = capi.library()
+    for name in declared:
+        assert isinstance(getattr(lib.raw, name), ctypes._CFuncPtr)
+    dynamic = subprocess.run(["nm", "-D", "--defined-only", str(capi.LIBRARY_PATH)],
+                             capture_output=True, text=True).stdout
+    for name in declared:
+        assert f" T {name}" in dynamic
+    assert lib.raw.sb200_version() >= 100
+
+
+def test_library_contains_sm100a_code_with_tma():
+    """The shipped kernels are sm_100a SASS and the hdiff/vadv fast paths really use TMA."""
+    out = subprocess.run(["cuobjdump", "-lelf", str(capi.LIBRARY_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", str(capi.LIBRARY_PATH)], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass          # cp.async.bulk.tensor
+    assert "LDG.E.128" in sass and "STG.E" in sass
+    assert "DFMA" in sass
+
+
+def test_failed_call_raises_with_stderr_message():
+    lib = capi.library()
+    with pytest.raises(cabi.ExecutionError, match="domain must be positive"):
+        lib.sb200_hdiff(capi.F64, None, None, None, 0, 4, 4, 1, 8, 64, 0, None, None)
+    with pytest.raises(cabi.ExecutionError, match="layout"):
+        lib.sb200_basic(capi.BASIC_COPY, capi.F64, None, None, 4, 4, 4, 2, 8, 64, 0, 0, 0, None, None)
+    with pytest.raises(cabi.ExecutionError, match="unsupported dtype"):
+        lib.sb200_stream_run(7, 16, 2, 0)
+
+
+def test_no_device_means_error_not_fallback():
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    bench = horizontal_diffusion.Fused(domain=(8, 8, 4), **CPU)
+    with pytest.raises(benchmark.ExecutionError, match="no CUDA device"):
+        bench.run()
+    with pytest.raises(benchmark.ParameterError, match="no CUDA device"):
+        horizontal_diffusion.Fused(domain=(8, 8, 4), verify=False)  # pinned host memory needs the device
+    with pytest.raises(benchmark.ExecutionError):
+        stream.Native(array_size=1024).run()
+
+
+def test_parameter_errors():
+    with pytest.raises(benchmark.ParameterError, match="layout"):
+        horizontal_diffusion.Fused(layout=(0, 1, 2), **CPU)
+    with pytest.raises(benchmark.ParameterError, match="at least 2"):
+        horizontal_diffusion.Fused(halo=(1, 2, 0), **CPU)
+    with pytest.raises(benchmark.ParameterError, match="positive halo"):
+        vertical_advection.Thomas(halo=(0, 3, 3), **CPU)
+    with pytest.raises(benchmark.ParameterError, match="positive halo"):
+        vertical_advection.Thomas(halo=(1, 0, 1), all_components=True, **CPU)
+    with pytest.raises(benchmark.ParameterError, match="positive halo"):
+        basic.OnesidedAverage(axis=1, halo=(1, 0, 1), **CPU)
+    with pytest.raises(benchmark.ParameterError, match="halo"):
+        basic.Laplacian(halo=(0, 1, 1), **CPU)
+    with pytest.raises(benchmark.ParameterError, match="at least one axis"):
+        basic.Laplacian(along_x=False, along_y=False, **CPU)
+    with pytest.raises(benchmark.ParameterError, match="dtype"):
+        basic.Copy(dtype="int32", **CPU)
+    with pytest.raises(benchmark.ParameterError):
+        basic.Copy(gpu_architecture="sm_90", **CPU)
+    with pytest.raises(benchmark.ParameterError, match="not divisible"):
+        basic.Copy(alignment=12, **CPU)
+    if not benchmark.HAVE_REFERENCE:
+        with pytest.raises(benchmark.ParameterError, match="verify"):
+            basic.Copy(pinned=False)  # verify defaults to True and needs the reference's oracle
+
+
+@pytest.mark.parametrize("dtype,alignment", [("float64", 128), ("float32", 128), ("float64", 0)])
+def test_field_layout_matches_reference_rules(dtype, alignment):
+    bench = horizontal_diffusion.Fused(domain=(128, 128, 80), dtype=dtype, alignment=alignment, **CPU)
+    data = bench.data()
+    assert data._fields == ("inp", "coeff", "out")
+    size = np.dtype(dtype).itemsize
+    sx, sy, sz = bench.strides
+    assert sx == 1 and sz == sy * 134
+    if alignment:
+        # 134-long rows pad to 144 (f64) / 160 (f32); first interior element aligned
+        assert sy == {8: 144, 4: 160}[size]
+        for field in data:
+            interior = field.ctypes.data + sum(s * h for s, h in zip(field.strides, bench.halo))
+            assert interior % alignment == 0
+    else:
+        assert sy == 134
+    assert all(f.shape == (134, 134, 86) for f in data)
+    assert all(0 <= f.min() and f.max() < 1 for f in data)
+    assert bench.geometry() == (128, 128, 80, 1, sy, sz)
+
+
+def test_seeded_fields_reproduce():
+    a = basic.Copy(domain=(9, 7, 5), seed=3, **CPU).data()
+    b = basic.Copy(domain=(9, 7, 5), seed=3, **CPU).data()
+    c = basic.Copy(domain=(9, 7, 5), seed=4, **CPU).data()
+    assert np.array_equal(a.inp, b.inp) and not np.array_equal(a.inp, c.inp)
+    assert not np.array_equal(a.inp, a.out)
+
+
+def test_byte_accounting_at_baseline_sizes():
+    """sbench figures and algorithmic minima."""
+    hd = horizontal_diffusion.Fused(domain=(128, 128, 80), **CPU)
+    assert hd.data_size == 32680448
+    # pure arithmetic for the large configs (constructing them would allocate tens of GB)
+    class Shape:
+        dtype = "float64"
+        all_components = False
+    big = Shape()
+    big.domain = (2048, 2048, 80)
+    assert horizontal_diffusion.HorizontalDiffusionMixin.algorithmic_bytes.fget(big) == 8063559680
+    big.domain = (1024, 1024, 160)
+    assert vertical_advection.VerticalAdvectionMixin.algorithmic_bytes.fget(big) == 8053063680
+    va = vertical_advection.Thomas(domain=(16, 16, 8), **CPU)
+    assert va.data_size == 10 * 16 * 16 * 8 * 8 and va.algorithmic_bytes == 6 * 16 * 16 * 8 * 8
+    assert va.data()._fields == ("ustage", "upos", "utens", "utensstage", "wcon", "ccol", "dcol", "datacol")
+    va3 = vertical_advection.Thomas(domain=(16, 16, 8), all_components=True, **CPU)
+    assert len(va3.args) == 16 and va3.data_size == 20 * 16 * 16 * 8 * 8
+
+
+def test_stream_array_size_is_padded_with_a_warning():
+    with pytest.warns(UserWarning, match="adapting array size"):
+        s = stream.Native(array_size=1000001)
+    assert s.array_size == 1000016
+    assert stream.Native(array_size=1 << 20).array_size == 1 << 20
+    with pytest.raises(benchmark.ParameterError):
+        stream.Native(ntimes=1)
+
+
+def test_fields_alloc_and_nbytes():
+    x = fields.alloc_array((2, 3), "int32", (1, 0))
+    assert x.strides == (4, 8)
+    y = fields.alloc_array((2, 3), "int32", (0, 1), alignment=64)
+    assert y.strides == (64, 4) and y.ctypes.data % 64 == 0 and fields.nbytes(y) == 76
+    z = fields.alloc_array((4, 5, 6), "float64", (2, 1, 0), 128, index_to_align=(1, 1, 1))
+    assert (z.ctypes.data + 8 + z.strides[1] + z.strides[2]) % 128 == 0
+    with pytest.raises(ValueError):
+        fields.alloc_array((2, 3), "int32", (0, 0))
+    assert cabi.data_ptr(z, (1, 1, 1)).value == z.ctypes.data + 8 + z.strides[1] + z.strides[2]
+    assert cabi.dtype_cname("float64") == "double" and cabi.dtype_cname("int16") == "std::int16_t"
