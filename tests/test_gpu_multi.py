@@ -1,0 +1,80 @@
+"""Two-GPU parity of the J-partitioned horizontal diffusion: NCCL halo exchange (CUDA pack /
+unpack kernels) + per-slab sweeps must reproduce the oracle on the global domain.
+Skipped on boxes with fewer than two GPUs."""
+
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import stencils
+from stencil_benchmarks_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, domain, results):
+    import torch
+    import torch.distributed as dist
+
+    from stencil_benchmarks_b200 import distributed
+    from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nx, ny_global, nz = domain
+        halo = (3, 3, 3)
+        rng = np.random.default_rng(21)
+        shape = tuple(d + 2 * h for d, h in zip(domain, halo))
+        g_inp, g_coeff = rng.random(shape), rng.random(shape)
+        start, ny = distributed.split_rows(ny_global, world)[rank]
+        bench = horizontal_diffusion.Fused(domain=(nx, ny, nz), halo=halo, verify=False, device=rank)
+        data = bench.data()
+        rows = slice(start, start + ny + 6)
+        data.inp[...] = g_inp[:, rows, :]
+        data.coeff[...] = g_coeff[:, rows, :]
+        lower, upper = distributed.neighbours(rank, world)
+        if lower is not None:
+            data.inp[:, :3, :] = -7.0  # must be replaced by the neighbour's rows
+        if upper is not None:
+            data.inp[:, 3 + ny:, :] = -7.0
+        mirrors = bench._device_fields(data)
+        bench.upload(data, mirrors)
+        ptr = {n: bench.interior_ptr(mirrors[n][1], h).value for n, h in zip(bench.args, data)}
+        _, _, _, _, sy, sz = bench.geometry()
+        exchange = distributed.cuda_halo_exchange(rank, world, "float64", nx, ny, nz, 3, sy, sz, width=3)
+        requests = exchange.start(ptr["inp"])
+        exchange.finish(ptr["inp"], requests)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        capi.library().sb200_hdiff(capi.F64, ptr["inp"], ptr["coeff"], ptr["out"], nx, ny, nz, 1, sy, sz,
+                                   0, None, stream)
+        torch.cuda.synchronize()
+        bench.download(data, mirrors)
+        expected = stencils.hdiff(g_inp, g_coeff)
+        ok = np.allclose(data.out[3:-3, 3:3 + ny, 3:-3], expected[3:-3, 3 + start:3 + start + ny, 3:-3],
+                         rtol=1e-13, atol=1e-14)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_hdiff_matches_global_oracle():
+    import torch
+    import torch.multiprocessing as mp
+
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    results = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), (300, 64, 5), results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}
