@@ -86,6 +86,70 @@ def configurations():
     ]
 
 
+def cuda_configurations():
+    """The reference's own GPU kernels, block sizes from scripts/sbench_h100_collection.py:113-152,
+    rendered for the BASELINE.json sizes and compiled for sm_100 ("the kernel to beat")."""
+    from stencil_benchmarks.benchmarks_collection.stencils.cuda_hip import (
+        basic,
+        horizontal_diffusion as hdiff,
+        vertical_advection as vadv,
+    )
+
+    common = dict(backend="cuda", compiler="nvcc", gpu_architecture="sm_100", verify=False,
+                  dry_runs=1, alignment=128, dtype="float64")
+    hd = dict(domain=(2048, 2048, 80), **common)
+    va = dict(domain=(1024, 1024, 160), **common)
+    ba = dict(domain=(1024, 1024, 80), halo=(1, 1, 1), loop="3D", block_size=(128, 2, 1), **common)
+    return [
+        ("cuda_hdiff_classic", hdiff.Classic, dict(block_size=(32, 12, 1), **hd)),
+        ("cuda_hdiff_otf", hdiff.OnTheFly, dict(block_size=(32, 16, 1), loop="3D", **hd)),
+        ("cuda_hdiff_otfincache", hdiff.OnTheFlyIncache, dict(block_size=(32, 8, 1), **hd)),
+        ("cuda_hdiff_jscansharedmem", hdiff.JScanSharedMem, dict(block_size=(256, 32, 1), **hd)),
+        ("cuda_hdiff_jscanotfincache", hdiff.JScanOtfIncache, dict(block_size=(128, 4, 1), **hd)),
+        ("cuda_hdiff_jscanotf", hdiff.JScanOtf, dict(block_size=(128, 4, 1), **hd)),
+        ("cuda_hdiff_jscanshuffleincache", hdiff.JScanShuffleIncache, dict(block_size=(28, 8, 2), **hd)),
+        ("cuda_hdiff_jscanshuffle", hdiff.JScanShuffle, dict(block_size=(28, 8, 2), **hd)),
+        ("cuda_hdiff_jscanshufflesystolic", hdiff.JScanShuffleSystolic, dict(block_size=(28, 4, 3), **hd)),
+        ("cuda_vadv_classic", vadv.Classic, dict(block_size=(128, 1), unroll_factor=8, **va)),
+        ("cuda_vadv_localmem", vadv.LocalMem, dict(block_size=(128, 1), unroll_factor=28, **va)),
+        ("cuda_vadv_sharedmem", vadv.SharedMem, dict(block_size=(64, 1), unroll_factor=0, **va)),
+        ("cuda_vadv_localmemmerged", vadv.LocalMemMerged, dict(block_size=(128, 1), unroll_factor=2, **va)),
+        ("cuda_basic_copy", basic.Copy, ba),
+        ("cuda_basic_avg_i", basic.OnesidedAverage, dict(axis=0, **ba)),
+        ("cuda_basic_lap_ij", basic.Laplacian, ba),
+    ]
+
+
+def build_cuda(captured, manifest):
+    """Render + cross-compile the reference's CUDA kernels (sm_100 SASS; runs on the GPU box)."""
+    for name, cls, kwargs in cuda_configurations():
+        try:
+            bench = cls(**kwargs)
+        except Exception as error:  # e.g. a variant that cannot be rendered for this size
+            print(f"skipped {name}: {error}")
+            continue
+        source = OUT / "src" / (name + ".cu")
+        source.write_text(captured["code"])
+        target = OUT / f"{name}.sm_100.so"
+        flags = [f for f in captured["command"][1:] if f not in ("-x", "cu")]
+        command = [captured["command"][0], "-o", str(target), "-x", "cu", str(source)] + flags + [
+            "-Xcompiler", "-shared", "-Xcompiler", "-fPIC"]
+        result = subprocess.run(command, capture_output=True, text=True)
+        if result.returncode != 0:
+            print(f"skipped {name}: does not compile for this configuration: "
+                  + result.stderr.strip().splitlines()[-1])
+            continue
+        manifest[name] = dict(
+            reference_class=f"{cls.__module__}.{cls.__name__}",
+            kwargs={k: (list(v) if isinstance(v, tuple) else v) for k, v in kwargs.items()},
+            args=list(bench.args), domain=list(bench.domain), halo=list(bench.halo),
+            strides=[int(s) for s in bench.strides], alignment=int(bench.alignment), dtype=bench.dtype,
+            data_size=int(bench.data_size), compile_flags=flags, libraries={"sm_100": target.name},
+        )
+        print(f"built {name}: strides {manifest[name]['strides']}")
+        del bench
+
+
 def main():
     if not REFERENCE.exists():
         print("no /root/reference here: keeping the prebuilt oracle/_ref as it is")
@@ -135,6 +199,7 @@ def main():
         )
         print(f"built {name}: strides {manifest[name]['strides']}")
         del bench
+    build_cuda(captured, manifest)
     (OUT / "manifest.json").write_text(json.dumps(manifest, indent=1))
     return 0
 
