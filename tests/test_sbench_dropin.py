@@ -1,0 +1,73 @@
+"""Drop-in check against the REAL reference package (dev container only; skipped elsewhere):
+with `stencil_benchmarks` importable, the B200 classes must subclass the reference's Benchmark,
+land in its REGISTRY, inherit its NumPy oracle and appear in its CLI tree."""
+
+import os
+import pathlib
+import subprocess
+import sys
+
+import pytest
+
+REFERENCE = pathlib.Path("/root/reference")
+SCRATCH = pathlib.Path("/tmp/sb200_reference_build")
+ROOT = pathlib.Path(__file__).parent.parent.resolve()
+
+pytestmark = pytest.mark.skipif(not REFERENCE.exists(), reason="reference tree not available")
+
+
+@pytest.fixture(scope="module")
+def reference_path():
+    marker = SCRATCH / ".built"
+    if not marker.exists():
+        # the same scratch build oracle/build_ref.py uses (two pybind11 helpers, ~20 s)
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import build_ref
+
+        build_ref.prepare_reference()
+    return str(SCRATCH)
+
+
+def run(code, reference_path, *argv):
+    env = dict(os.environ, PYTHONPATH=f"{reference_path}:{ROOT}")
+    return subprocess.run([sys.executable, "-c", code, *argv], capture_output=True, text=True, env=env,
+                          timeout=300, cwd="/tmp")
+
+
+def test_classes_register_in_the_reference(reference_path):
+    code = """
+import stencil_benchmarks.benchmark as ref
+import stencil_benchmarks.benchmarks_collection.stencils.base as ref_base
+import stencil_benchmarks_b200.benchmark as ours
+import stencil_benchmarks_b200.benchmarks_collection
+from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion, vertical_advection
+from stencil_benchmarks.cli import _cli_command
+assert ours.HAVE_REFERENCE and ours.REGISTRY is ref.REGISTRY and ours.Benchmark is ref.Benchmark
+assert issubclass(horizontal_diffusion.Fused, ref_base.HorizontalDiffusionStencil)
+assert horizontal_diffusion.Fused.verify_stencil is ref_base.HorizontalDiffusionStencil.verify_stencil
+assert horizontal_diffusion.Fused in ref.REGISTRY and vertical_advection.Thomas in ref.REGISTRY
+assert horizontal_diffusion.Fused.parameters["alignment"].default == 128
+print(" ".join(_cli_command(horizontal_diffusion.Fused)))
+b = horizontal_diffusion.Fused(domain=(10, 12, 5), pinned=False)   # verify=True is allowed here
+print(b.strides, b.verify)
+"""
+    result = run(code, reference_path)
+    assert result.returncode == 0, result.stderr
+    lines = result.stdout.strip().splitlines()
+    # _cli_command keeps module underscores; the click groups turn them into dashes (cli.py:230)
+    assert lines[0] == "stencils b200 horizontal_diffusion fused"
+    assert lines[1] == "(1, 16, 288) True"
+
+
+def test_sbench_cli_lists_the_backend(reference_path):
+    code = "import sys; from stencil_benchmarks_b200.scripts.sbench_b200 import main; sys.argv[0] = 'sbench'; main()"
+    top = run(code, reference_path, "stencils", "b200", "--help")
+    assert top.returncode == 0, top.stderr
+    for name in ("basic", "horizontal-diffusion", "vertical-advection"):
+        assert name in top.stdout
+    fused = run(code, reference_path, "stencils", "b200", "horizontal-diffusion", "fused", "--help")
+    assert fused.returncode == 0, fused.stderr
+    for option in ("--domain", "--halo", "--dtype", "--alignment", "--dry-runs", "--verify", "--seed"):
+        assert option in fused.stdout
+    stream = run(code, reference_path, "stream", "b200", "native", "--help")
+    assert stream.returncode == 0 and "--array-size" in stream.stdout
