@@ -103,6 +103,23 @@ int sb200_memcpy_d2h(void* hptr, const void* dptr, size_t nbytes, void* stream, 
 int sb200_memcpy_d2d(void* dst, const void* src, size_t nbytes, void* stream, int sync);
 int sb200_memset(void* dptr, int value, size_t nbytes, void* stream, int sync);
 
+/* Strided (2-D) copies: `height` rows of `width_bytes` bytes, row pitches in bytes
+ * (cudaMemcpy2DAsync).  Used to move j-slabs of a field: one "row" is the slab of one k level. */
+int sb200_memcpy2d_h2d(void* dptr, size_t dpitch, const void* hptr, size_t hpitch,
+                       size_t width_bytes, size_t height, void* stream);
+int sb200_memcpy2d_d2h(void* hptr, size_t hpitch, const void* dptr, size_t dpitch,
+                       size_t width_bytes, size_t height, void* stream);
+
+/* Streams and events for pipelining copies against sweeps (cudaStreamCreateWithFlags
+ * non-blocking, cudaEventCreate, cudaEventRecord, cudaStreamWaitEvent, cudaEventElapsedTime). */
+int sb200_stream_create(void** stream);
+int sb200_stream_destroy(void* stream);
+int sb200_event_create(void** event);
+int sb200_event_destroy(void* event);
+int sb200_event_record(void* event, void* stream);
+int sb200_stream_wait_event(void* stream, void* event);
+int sb200_event_elapsed(void* start, void* stop, double* seconds);
+
 /* cudaStreamSynchronize(stream) (stream == NULL: cudaDeviceSynchronize). */
 int sb200_synchronize(void* stream);
 

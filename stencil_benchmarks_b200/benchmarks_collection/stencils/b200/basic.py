@@ -22,10 +22,10 @@ class BasicStencilMixin(StencilMixin):
     def axis_and_mask(self):
         return 0, 0
 
-    def launch(self, pointers, dry_runs, time_ptr, stream):
+    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None):
         axis, mask = self.axis_and_mask()
         self._lib.sb200_basic(
-            self.kind, self._dtype_code, pointers["inp"], pointers["out"], *self.geometry(),
+            self.kind, self._dtype_code, pointers["inp"], pointers["out"], *self.geometry(domain),
             axis, mask, dry_runs, time_ptr, _vp(stream),
         )
 
@@ -53,6 +53,14 @@ class _AverageMixin(BasicStencilMixin):
     def axis_and_mask(self):
         return self.axis, 0
 
+    @property
+    def j_reach(self):
+        return int(self.axis == 1)
+
+    @property
+    def k_reach(self):
+        return int(self.axis == 2)
+
 
 class OnesidedAverage(_AverageMixin, base.OnesidedAverageStencil):
     alignment = _ALIGNMENT
@@ -75,3 +83,11 @@ class Laplacian(BasicStencilMixin, base.LaplacianStencil):
 
     def axis_and_mask(self):
         return 0, int(self.along_x) | int(self.along_y) << 1 | int(self.along_z) << 2
+
+    @property
+    def j_reach(self):
+        return int(self.along_y)
+
+    @property
+    def k_reach(self):
+        return int(self.along_z)

@@ -14,6 +14,7 @@ from .mixin import StencilMixin, _vp
 class HorizontalDiffusionMixin(StencilMixin):
     field_roles = {"inp": "in", "coeff": "in", "out": "out"}
     kernel_source = "hdiff.cu"
+    j_reach = 2
 
     @property
     def algorithmic_bytes(self):
@@ -21,10 +22,10 @@ class HorizontalDiffusionMixin(StencilMixin):
         nx, ny, nz = self.domain
         return int((2 * nx * ny * nz + (nx + 4) * (ny + 4) * nz) * np.dtype(self.dtype).itemsize)
 
-    def launch(self, pointers, dry_runs, time_ptr, stream):
+    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None):
         self._lib.sb200_hdiff(
             self._dtype_code, pointers["inp"], pointers["coeff"], pointers["out"],
-            *self.geometry(), dry_runs, time_ptr, _vp(stream),
+            *self.geometry(domain), dry_runs, time_ptr, _vp(stream),
         )
 
 

@@ -48,12 +48,18 @@ class StencilMixin(Benchmark):
     device = Parameter("CUDA device ordinal", 0)
     pinned = Parameter("allocate host fields in page-locked memory", True)
     seed = Parameter("seed of the random input fields (negative: non-deterministic)", 42)
+    chunks = Parameter(
+        "j-slabs over which host<->device copies and the sweep are pipelined on three streams "
+        "(1: upload everything, sweep once, download -- the reference's sequence)", 1)
 
     #: role of each field: "in" (H2D every run), "out" (D2H every run),
     #: "inout" (both), "scratch" (device only)
     field_roles = {}
     #: CUDA source shown by --print-code
     kernel_source = None
+    #: rows / levels of the INPUT fields a sweep reads beyond the rows / levels it writes
+    j_reach = 0
+    k_reach = 0
 
     def setup(self):
         if tuple(self.layout) != (2, 1, 0):
@@ -69,6 +75,8 @@ class StencilMixin(Benchmark):
             self._lib = capi.library()
         except cabi.CompilationError as error:
             raise ParameterError(*error.args) from error
+        if self.chunks < 1:
+            raise ParameterError("chunks must be at least 1")
         if self.pinned:
             try:
                 capi.require_device()
@@ -123,7 +131,9 @@ class StencilMixin(Benchmark):
         align = max(self.alignment, 256)
         for name, host in zip(self.args, data):
             nbytes = fields.nbytes(host)
-            buffer = capi.DeviceBuffer(nbytes + align)
+            # whole padded rows, so that slab copies may include the padding of the last row
+            extent = host.strides[2] * host.shape[2]
+            buffer = capi.DeviceBuffer(max(nbytes, extent) + align)
             # keep the host's alignment of the first interior element
             interior = sum(s * h for s, h in zip(host.strides, self.halo))
             first = buffer.ptr + (-(buffer.ptr + interior) % align)
@@ -152,8 +162,9 @@ class StencilMixin(Benchmark):
         capi.synchronize(stream)
 
     # ---- the run protocol -------------------------------------------------------
-    def launch(self, pointers, dry_runs, time_ptr, stream):
-        """Call the stencil's C entry point; ``pointers`` maps field name -> interior void*."""
+    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None):
+        """Call the stencil's C entry point; ``pointers`` maps field name -> interior void*;
+        ``domain`` overrides the swept domain (a j-slab of the fields)."""
         raise NotImplementedError
 
     @property
@@ -161,7 +172,117 @@ class StencilMixin(Benchmark):
         """Minimum HBM traffic of one sweep; defaults to the sbench figure."""
         return int(self.data_size)
 
+    def transfer_bytes(self):
+        """(H2D, D2H) bytes one run() moves, as counted from the copies it issues."""
+        data = self._data[0]
+        roles = [self.field_roles.get(name, "inout") for name in self.args]
+        if self.chunks == 1:
+            h2d = sum(fields.nbytes(f) for f, r in zip(data, roles) if r in ("in", "inout"))
+            d2h = sum(fields.nbytes(f) for f, r in zip(data, roles) if r in ("out", "inout"))
+            return h2d, d2h
+        ny, nz = int(self.domain[1]), int(self.domain[2])
+        size = np.dtype(self.dtype).itemsize
+        sy = int(self.strides[1])
+        jr, kr = min(self.j_reach, self.halo[1]), min(self.k_reach, self.halo[2])
+        up = (ny + 2 * jr) * sy * (nz + 2 * kr) * size
+        down = ny * sy * nz * size
+        return (up * sum(r in ("in", "inout") for r in roles),
+                down * sum(r in ("out", "inout") for r in roles))
+
+    # ---- pipelined execution ---------------------------------------------------------
+    def _pipeline(self):
+        """Three streams (upload, sweep, download) and per-slab events, created once."""
+        if getattr(self, "_pipe", None) is None:
+            def handle(create):
+                out = _vp()
+                create(ctypes.byref(out))
+                return out
+
+            n = self.chunks
+            self._pipe = dict(
+                streams=[handle(self._lib.sb200_stream_create) for _ in range(3)],
+                uploaded=[handle(self._lib.sb200_event_create) for _ in range(n)],
+                begin=[handle(self._lib.sb200_event_create) for _ in range(n)],
+                end=[handle(self._lib.sb200_event_create) for _ in range(n)],
+            )
+        return self._pipe
+
+    def _run_pipelined(self, data, mirrors):
+        """Upload slab c+1 while slab c is swept and slab c-1 is downloaded.
+
+        Slabs are ranges of j (rows stay contiguous; a slab of one level is one row of a
+        2-D copy whose pitch is the k stride).  Only the rows / levels a sweep reads are
+        uploaded, only interior rows / levels of the written fields are downloaded.
+        Returns the summed device time of the slab sweeps."""
+        raw = self._lib.raw
+
+        def check(status):
+            if status != 0:
+                raise cabi.ExecutionError("a CUDA call of the pipelined run failed (see stderr)")
+
+        pipe = self._pipeline()
+        s_up, s_run, s_down = pipe["streams"]
+        nx, ny, nz = (int(d) for d in self.domain)
+        hx, hy, hk = (int(h) for h in self.halo)
+        size = np.dtype(self.dtype).itemsize
+        _, sy, sz = (int(s) for s in self.strides)
+        jr, kr = min(self.j_reach, hy), min(self.k_reach, hk)
+        bounds = [ny * c // self.chunks for c in range(self.chunks + 1)]
+        plane0, planes_in = hk - kr, nz + 2 * kr
+        roles = [self.field_roles.get(name, "inout") for name in self.args]
+        frontier = hy - jr  # first array row not yet uploaded
+        for c in range(self.chunks):
+            j0, j1 = bounds[c], bounds[c + 1]
+            if j1 == j0:
+                continue
+            upto = j1 + hy + jr
+            upto = min(upto, ny + hy + jr)
+            for name, host, role in zip(self.args, data, roles):
+                if role in ("in", "inout") and upto > frontier:
+                    offset = (plane0 * sz + frontier * sy) * size
+                    check(raw.sb200_memcpy2d_h2d(
+                        _vp(mirrors[name][1] + offset), sz * size, _vp(host.ctypes.data + offset),
+                        sz * size, (upto - frontier) * sy * size, planes_in, s_up))
+            frontier = max(frontier, upto)
+            check(raw.sb200_event_record(pipe["uploaded"][c], s_up))
+            check(raw.sb200_stream_wait_event(s_run, pipe["uploaded"][c]))
+            pointers = {
+                name: _vp(self.interior_ptr(mirrors[name][1], host).value + j0 * sy * size)
+                for name, host in zip(self.args, data)
+            }
+            if self.dry_runs:
+                self.launch(pointers, self.dry_runs - 1, None, s_run.value, domain=(nx, j1 - j0, nz))
+            check(raw.sb200_event_record(pipe["begin"][c], s_run))
+            self.launch(pointers, 0, None, s_run.value, domain=(nx, j1 - j0, nz))
+            check(raw.sb200_event_record(pipe["end"][c], s_run))
+            check(raw.sb200_stream_wait_event(s_down, pipe["end"][c]))
+            for name, host, role in zip(self.args, data, roles):
+                if role in ("out", "inout"):
+                    offset = (hk * sz + (j0 + hy) * sy) * size
+                    check(raw.sb200_memcpy2d_d2h(
+                        _vp(host.ctypes.data + offset), sz * size, _vp(mirrors[name][1] + offset),
+                        sz * size, (j1 - j0) * sy * size, nz, s_down))
+        check(raw.sb200_synchronize(s_down))
+        check(raw.sb200_synchronize(s_up))
+        total = 0.0
+        elapsed = ctypes.c_double()
+        for c in range(self.chunks):
+            if bounds[c + 1] > bounds[c]:
+                check(raw.sb200_event_elapsed(pipe["begin"][c], pipe["end"][c], ctypes.byref(elapsed)))
+                total += elapsed.value
+        return total
+
     def run_stencil(self, data):
+        if self.chunks > 1:
+            try:
+                mirrors = self._device_fields(data)
+                t0 = _time.perf_counter()
+                sweep = self._run_pipelined(data, mirrors)
+                wall = _time.perf_counter() - t0
+            except cabi.ExecutionError as error:
+                raise ExecutionError(*error.args) from error
+            return {"time": sweep, "time-end-to-end": wall,
+                    "bandwidth-algorithmic": self.algorithmic_bytes / sweep / 1e9}
         try:
             mirrors = self._device_fields(data)
             t0 = _time.perf_counter()
@@ -194,6 +315,7 @@ class StencilMixin(Benchmark):
             "bandwidth-algorithmic": self.algorithmic_bytes / elapsed.value / 1e9,
         }
 
-    def geometry(self):
+    def geometry(self, domain=None):
         """(nx, ny, nz, sx, sy, sz) as the C ABI expects them (element strides)."""
-        return tuple(int(d) for d in self.domain) + tuple(int(s) for s in self.strides)
+        domain = self.domain if domain is None else domain
+        return tuple(int(d) for d in domain) + tuple(int(s) for s in self.strides)

@@ -37,7 +37,11 @@ class VerticalAdvectionMixin(StencilMixin):
         fields_moved = 6 if not self.all_components else 16
         return int(fields_moved * np.prod(self.domain) * np.dtype(self.dtype).itemsize)
 
-    def launch(self, pointers, dry_runs, time_ptr, stream):
+    @property
+    def j_reach(self):
+        return int(self.all_components)  # the v solve reads wcon(i, j+1)
+
+    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None):
         variant = {"auto": capi.VADV_AUTO, "global": capi.VADV_GLOBAL,
                    "onchip": capi.VADV_ONCHIP}[self.coefficients]
         components = [("u", 1, 0)]
@@ -49,7 +53,7 @@ class VerticalAdvectionMixin(StencilMixin):
             self._lib.sb200_vadv(
                 self._dtype_code, pointers[c + "stage"], pointers[c + "pos"], pointers[c + "tens"],
                 pointers[c + "tensstage"], pointers["wcon"], pointers["ccol"], pointers["dcol"],
-                pointers["datacol"], *self.geometry(), ishift, jshift, variant,
+                pointers["datacol"], *self.geometry(domain), ishift, jshift, variant,
                 dry_runs, ctypes.byref(elapsed) if time_ptr is not None else None, _vp(stream),
             )
             total += elapsed.value

@@ -55,6 +55,15 @@ PROTOTYPES = {
     "sb200_memcpy_d2h": (_i, [_vp, _vp, _sz, _vp, _i]),
     "sb200_memcpy_d2d": (_i, [_vp, _vp, _sz, _vp, _i]),
     "sb200_memset": (_i, [_vp, _i, _sz, _vp, _i]),
+    "sb200_memcpy2d_h2d": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "sb200_memcpy2d_d2h": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "sb200_stream_create": (_i, [ctypes.POINTER(_vp)]),
+    "sb200_stream_destroy": (_i, [_vp]),
+    "sb200_event_create": (_i, [ctypes.POINTER(_vp)]),
+    "sb200_event_destroy": (_i, [_vp]),
+    "sb200_event_record": (_i, [_vp, _vp]),
+    "sb200_stream_wait_event": (_i, [_vp, _vp]),
+    "sb200_event_elapsed": (_i, [_vp, _vp, _dp]),
     "sb200_synchronize": (_i, [_vp]),
     "sb200_flush_l2": (_i, [_vp]),
     "sb200_launch_count": (_u64, []),

@@ -131,6 +131,65 @@ int sb200_memset(void* dptr, int value, size_t nbytes, void* stream, int sync) {
   return 0;
 }
 
+int sb200_memcpy2d_h2d(void* dptr, size_t dpitch, const void* hptr, size_t hpitch, size_t width_bytes,
+                       size_t height, void* stream) {
+  SB200_CHECK(cudaMemcpy2DAsync(dptr, dpitch, hptr, hpitch, width_bytes, height, cudaMemcpyHostToDevice,
+                                static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sb200_memcpy2d_d2h(void* hptr, size_t hpitch, const void* dptr, size_t dpitch, size_t width_bytes,
+                       size_t height, void* stream) {
+  SB200_CHECK(cudaMemcpy2DAsync(hptr, hpitch, dptr, dpitch, width_bytes, height, cudaMemcpyDeviceToHost,
+                                static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sb200_stream_create(void** stream) {
+  if (stream == nullptr) return fail("sb200_stream_create: stream is NULL");
+  cudaStream_t s;
+  SB200_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = s;
+  return 0;
+}
+
+int sb200_stream_destroy(void* stream) {
+  SB200_CHECK(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sb200_event_create(void** event) {
+  if (event == nullptr) return fail("sb200_event_create: event is NULL");
+  cudaEvent_t e;
+  SB200_CHECK(cudaEventCreate(&e));
+  *event = e;
+  return 0;
+}
+
+int sb200_event_destroy(void* event) {
+  SB200_CHECK(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+  return 0;
+}
+
+int sb200_event_record(void* event, void* stream) {
+  SB200_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sb200_stream_wait_event(void* stream, void* event) {
+  SB200_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(event), 0));
+  return 0;
+}
+
+int sb200_event_elapsed(void* start, void* stop, double* seconds) {
+  if (seconds == nullptr) return fail("sb200_event_elapsed: seconds is NULL");
+  float ms = 0.f;
+  SB200_CHECK(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+  SB200_CHECK(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+  *seconds = double(ms) / 1000.0;
+  return 0;
+}
+
 int sb200_synchronize(void* stream) {
   if (stream == nullptr)
     SB200_CHECK(cudaDeviceSynchronize());

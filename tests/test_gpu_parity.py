@@ -214,3 +214,61 @@ def test_vadv_full_size():
         sl = (inner[0], inner[1], slice(inner[2].start + k, inner[2].start + k + 16))
         bad += np.count_nonzero(~np.isclose(data.utensstage[sl], expected[sl], rtol=1e-5, atol=1e-8))
     assert bad == 0
+
+
+# --------------------------------------------------------------------------------------
+# pipelined execution (chunks > 1): slab-wise upload / sweep / download on three streams
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("chunks", [2, 5])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_pipelined_hdiff(chunks, dtype):
+    bench = horizontal_diffusion.Fused(domain=(300, 67, 6), halo=(3, 3, 2), dtype=dtype, verify=False,
+                                       seed=17, chunks=chunks)
+    before = snapshot(bench)
+    result = bench.run()
+    assert result["time"] > 0 and result["time-end-to-end"] >= result["time"]
+    inner = bench.inner_slice()
+    expected = stencils.hdiff(before["inp"], before["coeff"])[inner]
+    assert close(bench.data().out[inner], expected, dtype)
+    check_inputs_untouched(bench, before, ["out"])
+    mask = np.ones(before["out"].shape, bool)
+    mask[inner] = False
+    assert np.array_equal(bench.data().out[mask], before["out"][mask])
+    # a second run on the same instance reuses streams, events and device mirrors
+    bench.run()
+    assert close(bench.data().out[inner], expected, dtype)
+
+
+@pytest.mark.parametrize("all_components", [False, True])
+def test_pipelined_vadv(all_components):
+    halo = (1, 1, 1)
+    bench = vertical_advection.Thomas(domain=(200, 37, 24), halo=halo, verify=False, seed=8, chunks=4,
+                                      all_components=all_components)
+    before = snapshot(bench)
+    bench.run()
+    inner = bench.inner_slice()
+    shifts = {"u": (1, 0), "v": (0, 1), "w": (0, 0)}
+    for c in ("uvw" if all_components else "u"):
+        expected = stencils._vadv_component(
+            before[c + "stage"], before[c + "pos"], before[c + "tens"], before[c + "tensstage"],
+            before["wcon"], halo, *shifts[c])[inner]
+        assert close(getattr(bench.data(), c + "tensstage")[inner], expected, "float64"), c
+    check_inputs_untouched(bench, before, [c + "tensstage" for c in "uvw"])
+
+
+def test_pipelined_basic():
+    halo = (1, 1, 1)
+    for extra, oracle in [
+        (dict(along_x=True, along_y=True, along_z=True), lambda f: stencils.laplacian(f, halo, (1, 1, 1))),
+        (dict(along_x=False, along_y=True, along_z=False), lambda f: stencils.laplacian(f, halo, (0, 1, 0))),
+    ]:
+        bench = basic.Laplacian(domain=(130, 50, 9), halo=halo, verify=False, seed=2, chunks=3, **extra)
+        before = snapshot(bench)
+        bench.run()
+        inner = bench.inner_slice()
+        assert close(bench.data().out[inner], oracle(before["inp"])[inner], "float64")
+    bench = basic.OnesidedAverage(domain=(64, 33, 5), halo=halo, axis=1, verify=False, chunks=4)
+    before = snapshot(bench)
+    bench.run()
+    inner = bench.inner_slice()
+    assert close(bench.data().out[inner], stencils.onesided_average(before["inp"], halo, 1)[inner], "float64")
