@@ -130,6 +130,7 @@ def time_reference(workload, steps, warmup, budget_s=None):
     cfg = WORKLOADS[workload]
     if not ref_cpu.available():
         raise RuntimeError("oracle/_ref is not built (run oracle/build_ref.py in the dev container)")
+    ref_cpu.use_all_cores()
     best = None
     for name in cfg["reference_kernels"]:
         kernel = ref_cpu.Kernel(name)
@@ -383,7 +384,7 @@ def extra_kernels(lib, capi, args):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=50)
+    parser.add_argument("--steps", type=int, default=200)
     parser.add_argument("--warmup", type=int, default=5)
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
     parser.add_argument("--workload", default="hdiff", choices=sorted(WORKLOADS))

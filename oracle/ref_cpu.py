@@ -100,8 +100,33 @@ class Kernel:
         return elapsed.value
 
 
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_cores():
+    """Make the OpenMP kernels use every core this process may run on.
+
+    torchrun exports OMP_NUM_THREADS=1 for its workers; the reference arm is meant to use all
+    host threads, so the setting is overridden in the environment (for a runtime that is not
+    loaded yet) and through omp_set_num_threads (for one that is)."""
+    n = usable_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def threads():
-    return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    try:
+        return int(ctypes.CDLL("libgomp.so.1").omp_get_max_threads())
+    except OSError:
+        return int(os.environ.get("OMP_NUM_THREADS", usable_cores()))
 
 
 def time_kernel(name, budget_s=10.0, warmup=1, seed=0):
