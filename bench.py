@@ -215,7 +215,10 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the exchange must not queue behind the interior sweep's CTAs: NCCL's own stream and the
+        # communication stream below get high priority
+        options = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=options)
     else:
         dist = None
 
@@ -235,7 +238,7 @@ def run_b200(args):
     raw = lib.raw
 
     main_stream = torch.cuda.current_stream()
-    comm_stream = torch.cuda.Stream()
+    comm_stream = torch.cuda.Stream(priority=-1)
     exchange = None
     if args.workload == "hdiff" and world > 1:
         exchange = distributed.cuda_halo_exchange(rank, world, cfg["dtype"], nx, ny, nz, cfg["halo"][0],

@@ -272,3 +272,32 @@ def test_pipelined_basic():
     bench.run()
     inner = bench.inner_slice()
     assert close(bench.data().out[inner], stencils.onesided_average(before["inp"], halo, 1)[inner], "float64")
+
+
+def test_resident_mode_and_wall_timer():
+    """resident=True uploads once and leaves results on the device; repeated in-place sweeps then
+    compose (vadv's utensstage is in/out), and the wall-clock timer reports a positive time."""
+    halo = (1, 1, 1)
+    bench = vertical_advection.Thomas(domain=(96, 20, 12), halo=halo, verify=False, seed=4, resident=True,
+                                      timers="wall")
+    before = snapshot(bench)
+    assert bench.run()["time"] > 0
+    bench.run()
+    mirrors = bench._device_fields(bench.data())
+    bench.download(bench.data(), mirrors)
+    once = stencils.vadv(before["ustage"], before["upos"], before["utens"], before["utensstage"],
+                         before["wcon"], halo)
+    twice = stencils.vadv(before["ustage"], before["upos"], before["utens"], once, before["wcon"], halo)
+    inner = bench.inner_slice()
+    assert close(bench.data().utensstage[inner], twice[inner], "float64")
+
+
+def test_data_sets_cycle():
+    bench = basic.Copy(domain=(40, 12, 6), verify=False, data_sets=2, seed=9)
+    first, second = bench.data(0), bench.data(1)
+    assert not np.array_equal(first.inp, second.inp)
+    bench.run()
+    bench.run()
+    inner = bench.inner_slice()
+    assert np.array_equal(first.out[inner], first.inp[inner])
+    assert np.array_equal(second.out[inner], second.inp[inner])
