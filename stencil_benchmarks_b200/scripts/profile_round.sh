@@ -17,7 +17,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:hdif
     -o $out/hdiff_tma_${tag} $KB --what hdiff --dtypes float64 --repeat 1 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:vadv_onchip -c 1 \
     -o $out/vadv_onchip_${tag} $KB --what vadv --dtypes float64 --repeat 1 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 9 -c 1 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 6 -c 1 \
     -o $out/stream_triad_${tag} $KB --what stream --dtypes float64 --repeat 1 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:basic_kernel -s 14 -c 1 \
     -o $out/basic_lap_${tag} $KB --what basic --dtypes float64 --repeat 1 > /dev/null 2>&1
@@ -29,6 +29,14 @@ for cfg in 256,1,16,1 256,2,16,1 256,4,16,1 512,2,16,1 512,4,16,1 512,4,16,0 512
   SB200_STREAM_CFG=$cfg timeout 120 $KB --what stream --dtypes float64 --repeat 10 --stream-log2 28 2>&1 | tail -4
 done > $out/stream_sweep_${tag}.log 2>&1
 
-# 4. all kernels, both dtypes, for the table in DESIGN.md
+# 4. STREAM size sweep through the plugin class (BASELINE.json configs[1])
+timeout 600 python -m stencil_benchmarks_b200.scripts.stream_sweep --max-log2 30 \
+    --out $out/stream_sizes_${tag}.csv > $out/stream_sizes_${tag}.log 2>&1
+
+# 5. the reference's own CUDA kernels recompiled for sm_100 (oracle/_ref, built in the dev container)
+timeout 600 python -m oracle.ref_cuda --repeat 11 --out $out/reference_cuda_${tag}.json \
+    > $out/reference_cuda_${tag}.log 2>&1
+
+# 6. all kernels, both dtypes, for the table in profiles/README.md
 timeout 600 $KB --repeat 20 --out $out/kernels_${tag}.json > $out/kernels_${tag}.log 2>&1
 ls -la $out

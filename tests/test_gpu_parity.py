@@ -301,3 +301,79 @@ def test_data_sets_cycle():
     inner = bench.inner_slice()
     assert np.array_equal(first.out[inner], first.inp[inner])
     assert np.array_equal(second.out[inner], second.inp[inner])
+
+
+# --------------------------------------------------------------------------------------
+# kernel selection: every variant must give the same answer, and fall back where it cannot run
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("coefficients", ["auto", "global", "onchip"])
+def test_vadv_variants_agree(coefficients):
+    halo = (2, 2, 2)
+    bench = vertical_advection.Thomas(domain=(200, 11, 33), halo=halo, verify=False, seed=6,
+                                      coefficients=coefficients)
+    before = snapshot(bench)
+    bench.run()
+    expected = stencils.vadv(before["ustage"], before["upos"], before["utens"], before["utensstage"],
+                             before["wcon"], halo)
+    inner = bench.inner_slice()
+    assert close(bench.data().utensstage[inner], expected[inner], "float64")
+
+
+def test_vadv_tall_columns_fall_back_to_global_kernel():
+    """nz = 200 float64 exceeds the on-chip store (shared memory next to the TMA ring)."""
+    halo = (1, 1, 1)
+    bench = vertical_advection.Thomas(domain=(128, 6, 200), halo=halo, verify=False, seed=12)
+    before = snapshot(bench)
+    bench.run()
+    expected = stencils.vadv(before["ustage"], before["upos"], before["utens"], before["utensstage"],
+                             before["wcon"], halo)
+    inner = bench.inner_slice()
+    assert close(bench.data().utensstage[inner], expected[inner], "float64")
+    forced = vertical_advection.Thomas(domain=(128, 6, 200), halo=halo, verify=False, coefficients="onchip")
+    from stencil_benchmarks_b200 import benchmark
+
+    with pytest.raises(benchmark.ExecutionError):
+        forced.run()
+
+
+def test_vadv_onchip_needs_aligned_fields():
+    from stencil_benchmarks_b200 import benchmark
+
+    bench = vertical_advection.Thomas(domain=(131, 7, 9), halo=(1, 1, 1), alignment=0, verify=False,
+                                      coefficients="onchip")
+    with pytest.raises(benchmark.ExecutionError):
+        bench.run()
+
+
+@pytest.mark.parametrize("nx", [60, 127, 128, 129, 255, 256, 257, 511, 513])
+def test_hdiff_tile_edges(nx):
+    """Widths around the TMA tile (256 doubles) and the TMA / generic switch (128 doubles)."""
+    bench = horizontal_diffusion.Fused(domain=(nx, 21, 3), halo=(2, 2, 0), verify=False, seed=nx)
+    before = snapshot(bench)
+    bench.run()
+    inner = bench.inner_slice()
+    expected = stencils.hdiff(before["inp"], before["coeff"])[inner]
+    np.testing.assert_allclose(bench.data().out[inner], expected, rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("ny", [1, 2, 3, 5, 127, 129])
+def test_hdiff_short_marches(ny):
+    """Row counts around the pipeline depth (4 rows per stage) and the march length."""
+    for dtype in ("float64", "float32"):
+        bench = horizontal_diffusion.Fused(domain=(260, ny, 2), halo=(2, 2, 1), dtype=dtype, verify=False,
+                                           seed=ny)
+        before = snapshot(bench)
+        bench.run()
+        inner = bench.inner_slice()
+        expected = stencils.hdiff(before["inp"], before["coeff"])[inner]
+        assert close(bench.data().out[inner], expected, dtype)
+
+
+def test_basic_full_size_float32():
+    bench = basic.Laplacian(domain=(1024, 1024, 80), halo=(1, 1, 1), dtype="float32", verify=False, seed=3)
+    data = bench.data()
+    bench.run()
+    expected = bench.empty_field()
+    native.laplacian(data.inp, expected, bench.halo, (True, True, False))
+    inner = bench.inner_slice()
+    assert close(data.out[inner], expected[inner], "float32")
