@@ -19,6 +19,7 @@
 // reads them back.  HBM traffic: 5 reads + 2 writes forward, 3 reads + 1 write
 // backward.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -183,6 +184,105 @@ __device__ __forceinline__ void tmem_load(uint32_t taddr, float& v) {
   v = __uint_as_float(bits);
 }
 
+// (c, e) pairs in adjacent TMEM columns: one LDTM / STTM per level
+__device__ __forceinline__ void tmem_store_pair(uint32_t taddr, double c, double e) {
+  const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
+  const unsigned long long eb = (unsigned long long)__double_as_longlong(e);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr),
+               "r"((uint32_t)(cb & 0xffffffffull)), "r"((uint32_t)(cb >> 32)),
+               "r"((uint32_t)(eb & 0xffffffffull)), "r"((uint32_t)(eb >> 32)));
+}
+__device__ __forceinline__ void tmem_store_pair(uint32_t taddr, float c, float e) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr),
+               "r"(__float_as_uint(c)), "r"(__float_as_uint(e)));
+}
+__device__ __forceinline__ void tmem_load_pair(uint32_t taddr, double& c, double& e) {
+  uint32_t c0, c1, e0, e1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(c0), "=r"(c1), "=r"(e0), "=r"(e1)
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(c0), "+r"(c1), "+r"(e0), "+r"(e1));
+  c = __longlong_as_double((long long)(((unsigned long long)c1 << 32) | c0));
+  e = __longlong_as_double((long long)(((unsigned long long)e1 << 32) | e0));
+}
+__device__ __forceinline__ void tmem_load_pair(uint32_t taddr, float& c, float& e) {
+  uint32_t cb, eb;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(cb), "=r"(eb) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(cb), "+r"(eb));
+  c = __uint_as_float(cb);
+  e = __uint_as_float(eb);
+}
+
+// Per-thread store of the eliminated coefficients (c[k], e[k]) by slot.  The first `paired`
+// slots keep both values in TMEM (adjacent columns); the remaining slots keep c in TMEM and e in
+// shared memory.  TMEM holds 512 32-bit columns per thread, so for float64 and nz = 160 that is
+// 97 paired slots + 62 split slots -- which leaves ~160 KB of shared memory to the TMA ring.
+template <class T>
+struct VadvSlots {
+  static constexpr int TCOLS = int(sizeof(T)) / 4;
+  uint32_t tmem;  // TMEM address of this warp's lane quarter, column 0 of the allocation
+  T* smem;        // this thread's column of the shared-memory part: slot q at smem[q * kCols]
+  int paired;
+
+  // KIND: 0 = slot known to be split, 1 = known to be paired, 2 = decide at run time
+  template <int KIND>
+  __device__ __forceinline__ void load(int p, T& c, T& e) const {
+    if (KIND == 1 || (KIND == 2 && p < paired)) {
+      tmem_load_pair(tmem + uint32_t(2 * TCOLS * p), c, e);
+    } else {
+      tmem_load(tmem + uint32_t(2 * TCOLS * paired + TCOLS * (p - paired)), c);
+      e = smem[(p - paired) * vcfg::kCols];
+    }
+  }
+  template <int KIND>
+  __device__ __forceinline__ void store(int p, T c, T e) const {
+    if (KIND == 1 || (KIND == 2 && p < paired)) {
+      tmem_store_pair(tmem + uint32_t(2 * TCOLS * p), c, e);
+    } else {
+      tmem_store(tmem + uint32_t(2 * TCOLS * paired + TCOLS * (p - paired)), c);
+      smem[(p - paired) * vcfg::kCols] = e;
+    }
+  }
+};
+
+// The slots of one chunk: level r of the chunk uses slot p + r*dp.  For the two pure kinds the
+// TMEM column and the shared-memory offset are affine in r with uniform coefficients, so the
+// unrolled body addresses them without per-thread integer work.
+template <class T, int KIND>
+struct VadvCursor {
+  static constexpr int TCOLS = VadvSlots<T>::TCOLS;
+  const VadvSlots<T>& slots;
+  int p, dp;
+  __device__ __forceinline__ VadvCursor(const VadvSlots<T>& s, int p_, int dp_) : slots(s), p(p_), dp(dp_) {}
+  __device__ __forceinline__ uint32_t column(int r) const {
+    const int q = p + r * dp;
+    return KIND == 1 ? uint32_t(2 * TCOLS * q) : uint32_t(2 * TCOLS * slots.paired + TCOLS * (q - slots.paired));
+  }
+  __device__ __forceinline__ T* shared(int r) const {
+    return slots.smem + (p + r * dp - slots.paired) * vcfg::kCols;
+  }
+  __device__ __forceinline__ void load(int r, T& c, T& e) const {
+    if (KIND == 1) {
+      tmem_load_pair(slots.tmem + column(r), c, e);
+    } else if (KIND == 0) {
+      tmem_load(slots.tmem + column(r), c);
+      e = *shared(r);
+    } else {
+      slots.template load<2>(p + r * dp, c, e);
+    }
+  }
+  __device__ __forceinline__ void store(int r, T c, T e) const {
+    if (KIND == 1) {
+      tmem_store_pair(slots.tmem + column(r), c, e);
+    } else if (KIND == 0) {
+      tmem_store(slots.tmem + column(r), c);
+      *shared(r) = e;
+    } else {
+      slots.template store<2>(p + r * dp, c, e);
+    }
+  }
+};
+
 // Reciprocal from the hardware seed (MUFU.RCP64H, ~2^-23) and two Newton steps: full double
 // precision up to the last ulp, no special-case branches, 5 FP64 instructions on the critical path
 // of nothing (the recurrence below is division free).
@@ -229,12 +329,11 @@ struct VadvForward {
 // eliminated and stored in slot `slot`, after the old column's level nz-1-s has been
 // back-substituted from the same slot.  FIRST: s may be 0 or 1 (resolved at compile time in the
 // peeled first chunk).
-template <class T, bool FIRST>
+template <class T, bool FIRST, int KIND>
 __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T v_pos, T v_tens,
-                                          T v_tss, T v_wsum, T& z, uint32_t tmem_slot, T* eslot,
+                                          T v_tss, T v_wsum, T& z, const VadvCursor<T, KIND>& slot, int r,
                                           T* old_out, bool old_valid) {
   using C = VadvConst<T>;
-  constexpr int TCOLS = int(sizeof(T)) / 4;
   const T dtr_stage = C::dtr_stage, bet_m = C::bet_m, bet_p = C::bet_p;
   f.wsum_cur = f.wsum_next;
   f.wsum_next = v_wsum;
@@ -275,13 +374,11 @@ __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T
   const T d = rn * rq;
   const T e = d - f.pos_cur - c * v_pos;  // folded right-hand side of level s-1
   // backward step of the old column on the slot that is about to be overwritten
-  T c_old;
-  tmem_load(tmem_slot, c_old);
-  z = *eslot - c_old * z;
+  T c_old, e_old;
+  slot.load(r, c_old, e_old);
+  z = e_old - c_old * z;
   if (old_valid) *old_out = dtr_stage * z;
-  tmem_store(tmem_slot, c);
-  *eslot = e;
-  (void)TCOLS;
+  slot.store(r, c, e);
   f.pos_cur = v_pos; f.tens_cur = v_tens; f.tss_cur = v_tss;
 }
 
@@ -293,19 +390,19 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
                        const __grid_constant__ CUtensorMap map_tensstage,
                        const __grid_constant__ CUtensorMap map_wcon, T* __restrict__ tensstage,
                        int nx, int ny, int nz, int64_t sy, int64_t sz, int ishift, int jshift,
-                       int stages) {
+                       int stages, int paired) {
   using C = VadvConst<T>;
   constexpr int COLS = vcfg::kCols;
   constexpr int TILE = vcfg::tile_bytes<T>(KD);           // one field, KD levels
   constexpr int WB = vcfg::wcon_width<T>();                // wcon tile width in elements
   constexpr int WTILE = vcfg::wcon_tile_bytes<T>(KD);
-  constexpr int TCOLS = int(sizeof(T)) / 4;                // TMEM columns per value
   const int STAGE = 4 * TILE + (jshift ? 2 : 1) * WTILE;
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: [ring: stages x STAGE][e store: (nz-1) x COLS][barriers][tmem base]
+  // layout: [ring: stages x STAGE][e store: (nz-1-paired) x COLS][barriers][tmem base]
   unsigned char* ring = smem;
   T* estore = reinterpret_cast<T*>(smem + stages * STAGE);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * STAGE + size_t(nz - 1) * COLS * sizeof(T));
+  uint64_t* full =
+      reinterpret_cast<uint64_t*>(smem + stages * STAGE + size_t(nz - 1 - paired) * COLS * sizeof(T));
   uint64_t* empty = full + stages;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(empty + stages);
 
@@ -371,8 +468,7 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
     // ===== compute warps =====
     const int t = threadIdx.x;
     const T dtr_stage = C::dtr_stage, bet_m = C::bet_m, bet_p = C::bet_p;
-    const uint32_t tmem_lane = *tmem_base_smem + (uint32_t(warp * 32) << 16);
-    T* ecol = estore + t;  // slot p at ecol[p * COLS]
+    const VadvSlots<T> slots{*tmem_base_smem + (uint32_t(warp * 32) << 16), estore + t, paired};
 
     VadvForward<T> f;
     T z = 0;                // backward state of the old column: x - pos of the level above
@@ -422,14 +518,12 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
 #pragma unroll
         for (int r = 0; r < KD; ++r) fetch(stage, r, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r]);
         release();
+        VadvCursor<T, 2> slot(slots, p0, dp);
 #pragma unroll
         for (int r = 0; r < KD; ++r) {
-          if (r < nz) {
-            const int pslot = p0 + dp * r;
-            vadv_step<T, true>(r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
-                               tmem_lane + uint32_t(pslot * TCOLS), ecol + pslot * COLS,
-                               old_base + int64_t(nz - 1 - r) * sz, old_valid);
-          }
+          if (r < nz)
+            vadv_step<T, true, 2>(r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z, slot, r,
+                                  old_base + int64_t(nz - 1 - r) * sz, old_valid);
         }
       }
       // ---- full chunks ----
@@ -442,27 +536,42 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
         for (int r = 0; r < KD; ++r) fetch(stage, r, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r]);
         release();
         rescale(f.p, f.r, f.q);
+        // the slots of a chunk are consecutive: all paired, all split, or (once per sweep) mixed;
+        // the two common cases run branch-free bodies
+        const int pa = p0 + dp * s0, pb = p0 + dp * (s0 + KD - 1);
+        const int kind = max(pa, pb) < paired ? 1 : (min(pa, pb) >= paired ? 0 : 2);
+        auto body = [&](auto kind_tag) {
+          constexpr int KIND = decltype(kind_tag)::value;
+          VadvCursor<T, KIND> slot(slots, pa, dp);
+          // output pointer of the old column: float64 schedules best when it is recomputed per
+          // level, float32 (issue bound) when it is carried (measured, profiles/vadv_tuning_r01.log)
+          T* out = old_base + int64_t(nz - 1 - s0) * sz;
 #pragma unroll
-        for (int r = 0; r < KD; ++r) {
-          const int s = s0 + r;
-          const int pslot = p0 + dp * s;
-          vadv_step<T, false>(s, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
-                              tmem_lane + uint32_t(pslot * TCOLS), ecol + pslot * COLS,
-                              old_base + int64_t(nz - 1 - s) * sz, old_valid);
-        }
+          for (int r = 0; r < KD; ++r) {
+            if (sizeof(T) == 8) out = old_base + int64_t(nz - 1 - (s0 + r)) * sz;
+            vadv_step<T, false, KIND>(s0 + r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
+                                      slot, r, out, old_valid);
+            if (sizeof(T) == 4) out -= sz;
+          }
+        };
+        if (kind == 1)
+          body(std::integral_constant<int, 1>{});
+        else if (kind == 0)
+          body(std::integral_constant<int, 0>{});
+        else
+          body(std::integral_constant<int, 2>{});
       }
       // ---- last, partial chunk ----
       if (s0 < nz) {
         tma::mbar_wait(&full[slot], round & 1);
         const unsigned char* stage = ring + slot * STAGE;
         rescale(f.p, f.r, f.q);
+        VadvCursor<T, 2> slot(slots, p0 + dp * s0, dp);
         for (int s = s0; s < nz; ++s) {
           T v_stage, v_pos, v_tens, v_tss, v_wsum;
           fetch(stage, s - s0, v_stage, v_pos, v_tens, v_tss, v_wsum);
-          const int pslot = p0 + dp * s;
-          vadv_step<T, false>(s, f, v_stage, v_pos, v_tens, v_tss, v_wsum, z,
-                              tmem_lane + uint32_t(pslot * TCOLS), ecol + pslot * COLS,
-                              old_base + int64_t(nz - 1 - s) * sz, old_valid);
+          vadv_step<T, false, 2>(s, f, v_stage, v_pos, v_tens, v_tss, v_wsum, z, slot, s - s0,
+                                 old_base + int64_t(nz - 1 - s) * sz, old_valid);
         }
         release();
       }
@@ -490,9 +599,9 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
       const int dp = dir ? -1 : 1;
       for (int s = 1; s <= nz - 1; ++s) {
         const int pslot = p0 + dp * s;
-        T c_old;
-        tmem_load(tmem_lane + uint32_t(pslot * TCOLS), c_old);
-        z = ecol[pslot * COLS] - c_old * z;
+        T c_old, e_old;
+        slots.template load<2>(pslot, c_old, e_old);
+        z = e_old - c_old * z;
         if (old_valid) old_base[int64_t(nz - 1 - s) * sz] = dtr_stage * z;
       }
     }
@@ -531,13 +640,20 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
   constexpr int KD = 4;
   constexpr int COLS = vcfg::kCols;
   *used = false;
-  // as many ring stages as fit next to the per-column store (at least 2, at most 4)
+  // TMEM: c of every slot, plus e of as many slots as the remaining columns hold
+  constexpr int TCOLS = int(sizeof(T)) / 4;
+  const int64_t slots = nz - 1;
+  if (slots * TCOLS > vcfg::kTmemCols) return 0;
+  int paired = int(std::min<int64_t>(slots, (vcfg::kTmemCols - slots * TCOLS) / TCOLS));
+  if (const char* env = std::getenv("SB200_VADV_PAIRED")) paired = std::min(paired, std::atoi(env));
+  int max_stages = 8;
+  if (const char* env = std::getenv("SB200_VADV_STAGES")) max_stages = std::max(2, std::atoi(env));
+  // as many ring stages as fit next to the shared-memory part of the store (2 ... 8)
   const size_t stage_size = 4 * vcfg::tile_bytes<T>(KD) + (jshift ? 2 : 1) * vcfg::wcon_tile_bytes<T>(KD);
-  const size_t fixed = size_t(nz - 1) * COLS * sizeof(T) + 128;
+  const size_t fixed = size_t(slots - paired) * COLS * sizeof(T) + 256;
   if (fixed + 2 * stage_size > 227 * 1024) return 0;
-  const int stages = int(std::min<size_t>(4, (227 * 1024 - fixed) / stage_size));
+  const int stages = int(std::min<size_t>(size_t(max_stages), (227 * 1024 - fixed) / stage_size));
   const size_t smem = stages * stage_size + fixed;
-  if ((nz - 1) * int64_t(sizeof(T) / 4) > vcfg::kTmemCols) return 0;
   const auto type = tma::tensor_type<T>();
   const uint64_t s1 = uint64_t(sy) * sizeof(T), s2 = uint64_t(sz) * sizeof(T);
   CUtensorMap m_stage, m_pos, m_tens, m_tss, m_wcon;
@@ -559,7 +675,7 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
   auto launch = [&] {
     vadv_onchip_kernel<T, KD><<<grid, vcfg::kThreads, smem, stream>>>(
         m_stage, m_pos, m_tens, m_tss, m_wcon, tensstage, int(nx), int(ny), int(nz), sy, sz, ishift, jshift,
-        stages);
+        stages, paired);
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);

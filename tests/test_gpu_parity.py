@@ -306,10 +306,11 @@ def test_data_sets_cycle():
 # --------------------------------------------------------------------------------------
 # kernel selection: every variant must give the same answer, and fall back where it cannot run
 # --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nz", [33, 200])  # 200: part of the store spills from TMEM to smem
 @pytest.mark.parametrize("coefficients", ["auto", "global", "onchip"])
-def test_vadv_variants_agree(coefficients):
+def test_vadv_variants_agree(coefficients, nz):
     halo = (2, 2, 2)
-    bench = vertical_advection.Thomas(domain=(200, 11, 33), halo=halo, verify=False, seed=6,
+    bench = vertical_advection.Thomas(domain=(200, 11, nz), halo=halo, verify=False, seed=6,
                                       coefficients=coefficients)
     before = snapshot(bench)
     bench.run()
@@ -320,16 +321,16 @@ def test_vadv_variants_agree(coefficients):
 
 
 def test_vadv_tall_columns_fall_back_to_global_kernel():
-    """nz = 200 float64 exceeds the on-chip store (shared memory next to the TMA ring)."""
+    """nz = 300 float64 exceeds the on-chip store (2 x 299 TMEM columns > 512)."""
     halo = (1, 1, 1)
-    bench = vertical_advection.Thomas(domain=(128, 6, 200), halo=halo, verify=False, seed=12)
+    bench = vertical_advection.Thomas(domain=(128, 6, 300), halo=halo, verify=False, seed=12)
     before = snapshot(bench)
     bench.run()
     expected = stencils.vadv(before["ustage"], before["upos"], before["utens"], before["utensstage"],
                              before["wcon"], halo)
     inner = bench.inner_slice()
     assert close(bench.data().utensstage[inner], expected[inner], "float64")
-    forced = vertical_advection.Thomas(domain=(128, 6, 200), halo=halo, verify=False, coefficients="onchip")
+    forced = vertical_advection.Thomas(domain=(128, 6, 300), halo=halo, verify=False, coefficients="onchip")
     from stencil_benchmarks_b200 import benchmark
 
     with pytest.raises(benchmark.ExecutionError):
