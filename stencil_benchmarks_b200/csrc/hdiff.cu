@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
     hdiff_tma_kernel(const __grid_constant__ CUtensorMap map_inp,
                      const __grid_constant__ CUtensorMap map_halo,
                      const __grid_constant__ CUtensorMap map_coeff, T* __restrict__ out, int nx,
-                     int ny, int jt, int64_t sy, int64_t sz) {
+                     int ny, int jt, int64_t sy, int64_t sz, int hint_mode) {
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
   constexpr int STAGE = tmacfg::stage_bytes(R);
@@ -241,15 +241,35 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
       tma::prefetch_tensormap(&map_halo);
       tma::prefetch_tensormap(&map_coeff);
       const int c0 = it / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
+      // Optional L2 policies (SB200_HDIFF_CFG third field): 1 = rows around a segment border
+      // evict_last, the rest evict_first; 2 = everything evict_first.  Both were measured and
+      // neither helps (profiles/hdiff_variants_r01.log: 1.286 / 1.238 ms vs 1.236 ms without
+      // hints), so the default is 0 = no hints.
+      const uint64_t keep = tma::policy_evict_last();
+      const uint64_t stream = tma::policy_evict_first();
       for (int n = 0; n < nstages; ++n) {
         const int slot = n % S;
         if (n >= S) tma::mbar_wait(&empty[slot], ((n / S) - 1) & 1);
         unsigned char* stage = smem + slot * STAGE;
-        tma::mbar_arrive_expect_tx(&full[slot], STAGE);
+        // the coeff rows of a stage belong to the output rows it completes: j = jb-4+nR+r; the
+        // first R = 4 rows of a segment complete nothing, so stage 0 carries no coeff tile
+        const bool with_coeff = (n + 1) * R > 4;
+        tma::mbar_arrive_expect_tx(&full[slot], with_coeff ? STAGE : STAGE - R * tmacfg::kRowBytes);
         // tensor origins: inp at (i = -16 B, j = -2), coeff at (i = 0, j = 0)
-        tma::load_3d(stage, &map_inp, c0, jb + n * R, k, &full[slot]);
-        tma::load_3d(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, jb + n * R, k, &full[slot]);
-        tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot]);
+        if (hint_mode == 0) {
+          tma::load_3d(stage, &map_inp, c0, jb + n * R, k, &full[slot]);
+          tma::load_3d(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, jb + n * R, k, &full[slot]);
+          if (with_coeff)
+            tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot]);
+        } else {
+          // rows jb-2 .. jb+1 (stage 0) and je-2 .. je+1 (last stage, possibly the one before) are shared
+          const bool border = hint_mode == 1 && (n == 0 || (n + 1) * R > je - jb);
+          const uint64_t policy = border ? keep : stream;
+          tma::load_3d_hint(stage, &map_inp, c0, jb + n * R, k, &full[slot], policy);
+          tma::load_3d_hint(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, jb + n * R, k, &full[slot], policy);
+          if (with_coeff)
+            tma::load_3d_hint(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot], stream);
+        }
       }
     }
     return;
@@ -329,17 +349,19 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
 struct HdiffConfig {
   int variant = 0;
   int jt = 0;
+  int hint_mode = 0;
 };
 
 inline HdiffConfig hdiff_config() {
   HdiffConfig cfg;
-  if (const char* env = std::getenv("SB200_HDIFF_CFG")) std::sscanf(env, "%d,%d", &cfg.variant, &cfg.jt);
+  if (const char* env = std::getenv("SB200_HDIFF_CFG"))
+    std::sscanf(env, "%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode);
   return cfg;
 }
 
 template <class T>
 int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
-                     int64_t sy, int64_t sz, int jt_request, int dry_runs, double* time,
+                     int64_t sy, int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
                      cudaStream_t stream, bool* used) {
   constexpr int R = 4, S = 3;
   constexpr int VEC = VecN<T>::value;
@@ -381,16 +403,13 @@ int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t n
   const dim3 grid(unsigned(xtiles), unsigned(ceil_div(ny, jt)), unsigned(nz));
   if (grid.y > 65535u || grid.z > 65535u) return fail("sb200_hdiff: domain too large for the launch grid");
   constexpr int smem = tmacfg::smem_bytes(R, S);
-  static bool configured = false;
-  if (!configured) {
-    SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S>,
+  // per launch: the attribute is per device, and a process may drive several devices
+  SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
   *used = true;
   auto launch = [&] {
     hdiff_tma_kernel<T, R, S><<<grid, tmacfg::kThreads, smem, stream>>>(map_inp, map_halo, map_coeff, out, int(nx),
-                                                                       int(ny), jt, sy, sz);
+                                                                       int(ny), jt, sy, sz, hint_mode);
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);
@@ -408,8 +427,8 @@ int launch_hdiff(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, i
   // TMA path: worth it once a 2 KB tile is at least half full
   if (vector_ok && cfg.variant != 1 && (cfg.variant == 2 || nx * int64_t(sizeof(T)) >= 1024)) {
     bool used = false;
-    const int rc = launch_hdiff_tma<T>(inp, coeff, out, nx, ny, nz, sy, sz, cfg.jt, dry_runs, time,
-                                       stream, &used);
+    const int rc = launch_hdiff_tma<T>(inp, coeff, out, nx, ny, nz, sy, sz, cfg.jt, cfg.hint_mode, dry_runs,
+                                       time, stream, &used);
     if (used || rc != 0) return rc;
   }
   const int vec = vector_ok ? V : 1;

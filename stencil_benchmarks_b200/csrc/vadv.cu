@@ -663,12 +663,9 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
       !tma::encode_3d(&m_tss, type, tensstage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
       !tma::encode_3d(&m_wcon, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::wcon_width<T>(), 1, KD))
     return 0;
-  static bool configured = false;
-  if (!configured) {
-    SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD>,
+  // per launch: the attribute is per device, and a process may drive several devices
+  SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
   const int64_t nbatches = ceil_div(nx, COLS) * ny;
   const unsigned grid = unsigned(std::min<int64_t>(nbatches, sm_count()));
   *used = true;
