@@ -40,12 +40,16 @@ WORKLOADS = {
                  reference_kernels=["vadv_kmiddlevec_1024x1024x160_f64",
                                     "vadv_kinnermostvec_1024x1024x160_f64"]),
 }
+TRIAD_N = 1 << 30  # BASELINE.json configs[1]: STREAM up to 2^30 float64 elements per array
 METRIC = {"hdiff": "horizontal-diffusion effective HBM bandwidth",
-          "vadv": "vertical-advection effective HBM bandwidth"}
+          "vadv": "vertical-advection effective HBM bandwidth",
+          "triad": "STREAM triad effective HBM bandwidth"}
 FALLBACK_PEAK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
 def algorithmic_bytes(workload, domain, itemsize=8):
+    if workload == "triad":
+        return 3 * TRIAD_N * itemsize
     nx, ny, nz = domain
     if workload == "hdiff":
         return (2 * nx * ny * nz + (nx + 4) * (ny + 4) * nz) * itemsize
@@ -124,8 +128,38 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference arm: the reference's OpenMP kernels (oracle/_ref) on the host cores
 # ------------------------------------------------------------------------------------------
+def time_reference_triad(steps, warmup, budget_s=None):
+    """CPU baseline of kind "port": the C restatement of the STREAM kernels (oracle/oracle.c) with
+    OpenMP on all host cores.  (The reference's CPU STREAM, stream/mc_calpin.py, is a separate
+    benchmark family that oracle/_ref does not build.)  Bounded sample: 2^28 elements per array."""
+    import numpy as np
+
+    from oracle import native, ref_cpu
+
+    threads = ref_cpu.use_all_cores()
+    n = 1 << 28
+    a, b, c = np.zeros(n), np.full(n, 2.0), np.full(n, 0.5)
+    for _ in range(max(warmup, 1)):
+        native.stream_triad(a, b, c)
+    times = []
+    start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        native.stream_triad(a, b, c)
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - start > budget_s:
+            break
+    mean = sum(times) / len(times)
+    return dict(name="oracle_stream_triad_f64 (OpenMP port)", isa="native gcc -O2", mean_s=mean,
+                sweeps=len(times), min_s=min(times), threads=threads, bytes=3 * n * 8, kind="port",
+                sample=f"{len(times)} triads over 2^28 float64 elements per array")
+
+
 def time_reference(workload, steps, warmup, budget_s=None):
     from oracle import ref_cpu
+
+    if workload == "triad":
+        return time_reference_triad(steps, warmup, budget_s)
 
     cfg = WORKLOADS[workload]
     if not ref_cpu.available():
@@ -156,20 +190,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = WORKLOADS[args.workload]
     best = time_reference(args.workload, args.steps, args.warmup)
-    nbytes = algorithmic_bytes(args.workload, cfg["domain"])
-    value = nbytes / best["mean_s"] / 1e9
-    sample = (f"{best['sweeps']} full sweeps of {'x'.join(map(str, cfg['domain']))} float64, reference "
-              f"OpenMP kernel {best['name']} ({best['isa']}), best of {len(cfg['reference_kernels'])} variants")
+    if args.workload == "triad":
+        value = best["bytes"] / best["mean_s"] / 1e9
+        sample = best["sample"]
+    else:
+        cfg = WORKLOADS[args.workload]
+        nbytes = algorithmic_bytes(args.workload, cfg["domain"])
+        value = nbytes / best["mean_s"] / 1e9
+        sample = (f"{best['sweeps']} full sweeps of {'x'.join(map(str, cfg['domain']))} float64, reference "
+                  f"OpenMP kernel {best['name']} ({best['isa']}), best of {len(cfg['reference_kernels'])} variants")
     line = {
         "impl": "reference",
         "metric": METRIC[args.workload], "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": best["sweeps"], "warmup": max(args.warmup, 1), "ms_per_step": best["mean_s"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args.workload, 1),
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": best["threads"], "kind": "reference",
-                         "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": best["threads"],
+                         "kind": best.get("kind", "reference"), "sample": sample},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,15 +215,28 @@ def run_reference(args):
     return 0
 
 
-def workload_config(workload, n_gpus):
+EXCHANGE_TEXT = {
+    "peer": "fused into the sweep: halo rows read by TMA from the neighbour GPU's HBM (CUDA IPC peer "
+            "memory over NVLink), every sweep, one kernel launch per sweep",
+    "nccl": "NCCL send/recv, width 3, every sweep, on a high-priority stream overlapped with the interior kernel",
+}
+
+
+def workload_config(workload, n_gpus, exchange=None):
+    if workload == "triad":
+        return {
+            "workload": f"STREAM triad a = b + 3c, {TRIAD_N} float64 elements per array per GPU",
+            "partition": "independent arrays per GPU, no communication",
+            "bytes_per_step_per_gpu": algorithmic_bytes("triad", None),
+            "l2": "arrays (3 x 8.6 GB per GPU) exceed the 126 MB L2; no flush between steps",
+        }
     cfg = WORKLOADS[workload]
     nx, ny, nz = cfg["domain"]
     return {
         "workload": f"{workload} {nx}x{ny}x{nz} float64 per GPU, halo 3, alignment 128",
         "global_domain": [nx, ny * n_gpus, nz],
         "partition": "J slabs, one per GPU" if n_gpus > 1 else "single GPU",
-        "halo_exchange": ("NCCL send/recv, width 3, every sweep, overlapped with the interior kernel"
-                          if workload == "hdiff" and n_gpus > 1 else "none"),
+        "halo_exchange": (EXCHANGE_TEXT.get(exchange, "none") if workload == "hdiff" and n_gpus > 1 else "none"),
         "bytes_per_step_per_gpu": algorithmic_bytes(workload, cfg["domain"]),
         "l2": "fields (8.7 GB hdiff / 11.3 GB vadv per GPU) exceed the 126 MB L2; no flush between steps",
     }
@@ -240,7 +291,11 @@ def run_b200(args):
     main_stream = torch.cuda.current_stream()
     comm_stream = torch.cuda.Stream(priority=-1)
     exchange = None
-    if args.workload == "hdiff" and world > 1:
+    peers = None
+    if args.workload == "hdiff" and world > 1 and args.exchange == "peer":
+        # fused exchange: neighbours' inp slabs mapped through CUDA IPC, halo rows read by TMA
+        peers = distributed.PeerSlabs(dist, rank, world, mirrors["inp"][0].ptr, pointers["inp"].value, ny, sz)
+    elif args.workload == "hdiff" and world > 1:
         exchange = distributed.cuda_halo_exchange(rank, world, cfg["dtype"], nx, ny, nz, cfg["halo"][0],
                                                   sy, sz, width=cfg["halo"][1])
         (lo, hi), strips = distributed.interior_and_boundary_rows(
@@ -258,6 +313,11 @@ def run_b200(args):
     def step():
         if args.workload == "vadv":
             bench.launch(pointers, 0, None, main_stream.cuda_stream)
+        elif peers is not None:
+            raw.sb200_hdiff_peer(code, pointers["inp"], pointers["coeff"], pointers["out"],
+                                 vp(peers.lower), peers.ny_lower, peers.sz_lower,
+                                 vp(peers.upper), peers.ny_upper, peers.sz_upper,
+                                 nx, ny, nz, 1, sy, sz, 0, None, vp(main_stream.cuda_stream))
         elif exchange is None:
             hdiff_rows(0, ny, main_stream)
         else:
@@ -277,6 +337,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()  # every rank has uploaded its fields before a neighbour reads them
     for _ in range(args.warmup):
         step()
     barrier()
@@ -322,7 +383,7 @@ def run_b200(args):
         "metric": METRIC[args.workload], "value": value, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.workload, world),
+        "data": "synthetic", "config": workload_config(args.workload, world, args.exchange),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
                      "peak_source": peak_source,
@@ -351,6 +412,103 @@ def run_b200(args):
             except Exception as error:  # the baseline must not lose the GPU numbers
                 line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count(),
                                         "kind": "reference", "sample": f"failed: {error}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        if peers is not None:
+            peers.close()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_triad(args):
+    """STREAM triad, one independent set of arrays per GPU (no communication)."""
+    import torch
+
+    from stencil_benchmarks_b200 import capi
+    from stencil_benchmarks_b200.benchmarks_collection.stream import b200 as stream
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: the B200 backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.library()
+    raw = lib.raw
+    n = TRIAD_N
+    buffers = [capi.DeviceBuffer(8 * n) for _ in range(3)]
+    ptrs = [ctypes.c_void_p(b.ptr) for b in buffers]
+    lib.sb200_stream_op(capi.STREAM_INIT, capi.F64, *ptrs, n, 3.0, 0, None, None)
+    stream_handle = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def step():
+        raw.sb200_stream_op(capi.STREAM_TRIAD, capi.F64, *ptrs, n, 3.0, 0, None, stream_handle)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches_before = capi.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            step()
+        stop.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = capi.launch_count() - launches_before
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    nbytes = algorithmic_bytes("triad", None)
+    achieved = nbytes / (ms_per_step * 1e-3) / 1e9
+    del buffers
+    # end to end = the plugin call: the reference's STREAM interface has no host data
+    # (stream/cuda_hip.py:121-144 runs init + kernels + verification on the device)
+    results = stream.Native(array_size=n, ntimes=5, dtype="float64", device=local_rank).run()
+    triad = next(r for r in results if r["name"] == "triad")
+    e2e_value = triad["bandwidth"] / 1e3
+    if dist is not None:
+        t = torch.tensor([e2e_value], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        e2e_value = float(t.item())
+    peak, peak_source = measured_peak()
+    line = {
+        "metric": METRIC["triad"], "value": world * achieved, "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config("triad", world),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": profiled_traffic("triad"),
+                     "peak_source": peak_source, "kernel": "stream_kernel<double, TRIAD>",
+                     "note": "per GPU; the denominator is a torch copy, a 2:1 read:write kernel reads above 1"},
+        "e2e": {"value": world * e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "how": "plugin call stream.b200.Native.run() (McCalpin table, min time over 4 rounds); "
+                       "the reference's STREAM interface keeps all data on the device"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "pct_of_nominal_8TBs": achieved / 8000.0,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        best = time_reference_triad(steps=20, warmup=1, budget_s=15.0)
+        line["cpu_baseline"] = {"value": best["bytes"] / best["mean_s"] / 1e9, "unit": "GB/s",
+                                "cores": best["threads"], "kind": "port", "sample": best["sample"]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -390,7 +548,10 @@ def main():
     parser.add_argument("--steps", type=int, default=200)
     parser.add_argument("--warmup", type=int, default=5)
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    parser.add_argument("--workload", default="hdiff", choices=sorted(WORKLOADS))
+    parser.add_argument("--workload", default="hdiff", choices=sorted(WORKLOADS) + ["triad"])
+    parser.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                        help="hdiff halo exchange at N > 1: fused into the sweep over peer memory, "
+                             "or NCCL send/recv on a second stream")
     parser.add_argument("--e2e-steps", type=int, default=3)
     parser.add_argument("--e2e-chunks", type=int, default=8)
     parser.add_argument("--no-extras", action="store_true")
@@ -401,6 +562,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "triad":
+        return run_triad(args)
     return run_b200(args)
 
 

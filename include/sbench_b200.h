@@ -201,6 +201,27 @@ int sb200_vadv(int dtype, const void* ustage, const void* upos, const void* uten
 /* Multi-GPU halo plumbing for the J-partitioned horizontal diffusion  */
 /* ------------------------------------------------------------------ */
 
+/* Peer memory across processes (one process per GPU): cudaIpcGetMemHandle on the BASE of a
+ * sb200_malloc allocation (64-byte handle, sent to the neighbour by any host channel),
+ * cudaIpcOpenMemHandle / cudaIpcCloseMemHandle on the receiving side.  The mapped pointer
+ * addresses the neighbour's HBM over NVLink. */
+int sb200_ipc_get_handle(const void* dptr, void* handle64);
+int sb200_ipc_open_handle(const void* handle64, void** dptr);
+int sb200_ipc_close_handle(void* dptr);
+
+/* Horizontal diffusion of one J slab with the halo exchange fused into the sweep: the two j-halo
+ * rows on each side are read by TMA directly from the neighbouring GPUs' slabs (`inp_lower` /
+ * `inp_upper`: pointers to the first interior element of the neighbour's inp field, mapped with
+ * sb200_ipc_open_handle; NULL = no neighbour, the local halo is used).  `ny_*` / `sz_*` are the
+ * neighbours' row counts and k strides (same i extent and j stride as the local slab).  One kernel
+ * launch per sweep, no pack / send / receive / unpack.  Requires 16-byte aligned fields (TMA). */
+int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, void* out,
+                     const void* inp_lower, int64_t ny_lower, int64_t sz_lower,
+                     const void* inp_upper, int64_t ny_upper, int64_t sz_upper,
+                     int64_t nx, int64_t ny, int64_t nz,
+                     int64_t sx, int64_t sy, int64_t sz,
+                     int dry_runs, double* time, void* stream);
+
 /* Pack `nrows` consecutive j-rows (all nz levels, i range [-hx, nx+hx)) of a
  * field into a contiguous buffer / unpack them again, so that one
  * ncclSend/ncclRecv moves a whole halo face.  `field` points to the first

@@ -180,7 +180,11 @@ constexpr int kConsumers = 128;
 constexpr int kThreads = kConsumers + 32;
 constexpr int kRowBytes = 2048;
 constexpr int kHaloBytes = 32;
-__host__ __device__ constexpr int stage_bytes(int rows) { return rows * (2 * kRowBytes + kHaloBytes); }
+// the halo region of a stage reserves 128 bytes per row: one R-row box packs its rows at 32 bytes,
+// the per-row boxes of the fused halo exchange need 128-byte aligned destinations
+constexpr int kHaloPitchEdge = 128;
+__host__ __device__ constexpr int stage_bytes(int rows) { return rows * (2 * kRowBytes + kHaloPitchEdge); }
+__host__ __device__ constexpr int stage_tx_bytes(int rows) { return rows * (2 * kRowBytes + kHaloBytes); }
 __host__ __device__ constexpr int smem_bytes(int rows, int stages) { return stages * stage_bytes(rows) + 2 * stages * 8; }
 }  // namespace tmacfg
 
@@ -205,11 +209,24 @@ __device__ __forceinline__ void read_strip(const unsigned char* a_row, const uns
   }
 }
 
-template <class T, int R, int S>
+// Fused halo exchange (multi-GPU): the j-halo rows of a slab are the edge rows of the neighbouring
+// GPUs' slabs.  Instead of copying them into the local halo first, the producer of an edge
+// segment fetches those rows straight from the neighbour's HBM over NVLink -- a TMA load on a
+// tensor map whose base is the peer allocation (CUDA IPC mapping) -- one row per box, so local and
+// remote rows of a stage can be mixed freely.  Index 0 = this GPU, 1 = lower, 2 = upper neighbour.
+struct PeerMaps {
+  CUtensorMap row_inp[3];   // box: 256 x 1 x 1 (8-byte elements)
+  CUtensorMap row_halo[3];  // box:   4 x 1 x 1
+  int ny_lower;             // rows of the lower neighbour's slab
+  int has_lower, has_upper;
+};
+
+template <class T, int R, int S, bool PEER>
 __global__ void __launch_bounds__(tmacfg::kThreads, 4)
     hdiff_tma_kernel(const __grid_constant__ CUtensorMap map_inp,
                      const __grid_constant__ CUtensorMap map_halo,
-                     const __grid_constant__ CUtensorMap map_coeff, T* __restrict__ out, int nx,
+                     const __grid_constant__ CUtensorMap map_coeff,
+                     const __grid_constant__ PeerMaps peer, T* __restrict__ out, int nx,
                      int ny, int jt, int64_t sy, int64_t sz, int hint_mode) {
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
@@ -240,6 +257,12 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
       tma::prefetch_tensormap(&map_inp);
       tma::prefetch_tensormap(&map_halo);
       tma::prefetch_tensormap(&map_coeff);
+      if (PEER) {
+        for (int w = 0; w < 3; ++w) {
+          tma::prefetch_tensormap(&peer.row_inp[w]);
+          tma::prefetch_tensormap(&peer.row_halo[w]);
+        }
+      }
       const int c0 = it / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
       // Optional L2 policies (SB200_HDIFF_CFG third field): 1 = rows around a segment border
       // evict_last, the rest evict_first; 2 = everything evict_first.  Both were measured and
@@ -254,9 +277,32 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
         // the coeff rows of a stage belong to the output rows it completes: j = jb-4+nR+r; the
         // first R = 4 rows of a segment complete nothing, so stage 0 carries no coeff tile
         const bool with_coeff = (n + 1) * R > 4;
-        tma::mbar_arrive_expect_tx(&full[slot], with_coeff ? STAGE : STAGE - R * tmacfg::kRowBytes);
+        tma::mbar_arrive_expect_tx(&full[slot], tmacfg::stage_tx_bytes(R) - (with_coeff ? 0 : R * tmacfg::kRowBytes));
         // tensor origins: inp at (i = -16 B, j = -2), coeff at (i = 0, j = 0)
-        if (hint_mode == 0) {
+        bool remote_rows = false;
+        if (PEER) {
+          const int q0 = jb - 2 + n * R;  // first inp row of the stage
+          remote_rows = (peer.has_lower && q0 < 0) || (peer.has_upper && q0 + R > ny);
+        }
+        if (PEER && remote_rows) {
+          // edge stage: row by row, each from the GPU that owns it
+          for (int r = 0; r < R; ++r) {
+            const int q = jb - 2 + n * R + r;
+            int who = 0, row = q;
+            if (peer.has_lower && q < 0) {
+              who = 1;
+              row = peer.ny_lower + q;
+            } else if (peer.has_upper && q >= ny) {
+              who = 2;
+              row = q - ny;
+            }
+            tma::load_3d(stage + r * tmacfg::kRowBytes, &peer.row_inp[who], c0, row + 2, k, &full[slot]);
+            tma::load_3d(stage + 2 * R * tmacfg::kRowBytes + r * tmacfg::kHaloPitchEdge, &peer.row_halo[who],
+                         c0 + 256, row + 2, k, &full[slot]);
+          }
+          if (with_coeff)
+            tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot]);
+        } else if (hint_mode == 0) {
           tma::load_3d(stage, &map_inp, c0, jb + n * R, k, &full[slot]);
           tma::load_3d(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, jb + n * R, k, &full[slot]);
           if (with_coeff)
@@ -295,11 +341,16 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
     const int slot = n % S;
     tma::mbar_wait(&full[slot], (n / S) & 1);
     const unsigned char* stage = smem + slot * STAGE;
+    int halo_pitch = tmacfg::kHaloBytes;
+    if (PEER) {
+      const int q0 = jb - 2 + n * R;
+      if ((peer.has_lower && q0 < 0) || (peer.has_upper && q0 + R > ny)) halo_pitch = tmacfg::kHaloPitchEdge;
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int j = jb + n * R + r - 4;  // output row completed by inp row j + 2
       read_strip<T, VEC>(stage + r * tmacfg::kRowBytes,
-                         stage + 2 * R * tmacfg::kRowBytes + r * tmacfg::kHaloBytes, t, rnn);
+                         stage + 2 * R * tmacfg::kRowBytes + r * halo_pitch, t, rnn);
       T cf[VEC];
       {
         const unsigned char* c_row = stage + R * tmacfg::kRowBytes + r * tmacfg::kRowBytes + 16 * t;
@@ -362,7 +413,9 @@ inline HdiffConfig hdiff_config() {
 template <class T>
 int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
                      int64_t sy, int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
-                     cudaStream_t stream, bool* used) {
+                     cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
+                     int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
+                     int64_t sz_upper = 0) {
   constexpr int R = 4, S = 3;
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
@@ -391,6 +444,27 @@ int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t n
                           uint64_t(sy) * sizeof(T), uint64_t(sz) * sizeof(T), 4, R, 1))
     return 0;
 
+  // fused halo exchange: per-row maps on this slab and on the neighbours' slabs
+  const bool with_peers = inp_lower != nullptr || inp_upper != nullptr;
+  PeerMaps peer;
+  peer.ny_lower = int(ny_lower);
+  peer.has_lower = inp_lower != nullptr;
+  peer.has_upper = inp_upper != nullptr;
+  if (with_peers) {
+    const T* bases[3] = {inp, inp_lower ? inp_lower : inp, inp_upper ? inp_upper : inp};
+    const int64_t rows[3] = {ny, inp_lower ? ny_lower : ny, inp_upper ? ny_upper : ny};
+    // slabs with different row counts have different k strides
+    const int64_t kstride[3] = {sz, inp_lower ? sz_lower : sz, inp_upper ? sz_upper : sz};
+    for (int w = 0; w < 3; ++w) {
+      const T* origin = bases[w] - 16 / int(sizeof(T)) - 2 * sy;
+      if (!tma::encode_3d_u64(&peer.row_inp[w], origin, inp_d0, uint64_t(rows[w] + 4), uint64_t(nz),
+                              uint64_t(sy) * sizeof(T), uint64_t(kstride[w]) * sizeof(T), 256, 1, 1) ||
+          !tma::encode_3d_u64(&peer.row_halo[w], origin, inp_d0, uint64_t(rows[w] + 4), uint64_t(nz),
+                              uint64_t(sy) * sizeof(T), uint64_t(kstride[w]) * sizeof(T), 4, 1, 1))
+        return fail("sb200_hdiff_peer: cannot encode the tensor maps of the neighbouring slabs");
+    }
+  }
+
   const int64_t xtiles = ceil_div(nx, TW);
   int jt = jt_request;
   if (jt <= 0) {
@@ -404,12 +478,18 @@ int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t n
   if (grid.y > 65535u || grid.z > 65535u) return fail("sb200_hdiff: domain too large for the launch grid");
   constexpr int smem = tmacfg::smem_bytes(R, S);
   // per launch: the attribute is per device, and a process may drive several devices
-  SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   *used = true;
   auto launch = [&] {
-    hdiff_tma_kernel<T, R, S><<<grid, tmacfg::kThreads, smem, stream>>>(map_inp, map_halo, map_coeff, out, int(nx),
-                                                                       int(ny), jt, sy, sz, hint_mode);
+    if (with_peers)
+      hdiff_tma_kernel<T, R, S, true><<<grid, tmacfg::kThreads, smem, stream>>>(
+          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), jt, sy, sz, hint_mode);
+    else
+      hdiff_tma_kernel<T, R, S, false><<<grid, tmacfg::kThreads, smem, stream>>>(
+          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), jt, sy, sz, hint_mode);
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);
@@ -452,6 +532,44 @@ int launch_hdiff(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, i
 }  // namespace sb200
 
 using namespace sb200;
+
+extern "C" int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, void* out,
+                                const void* inp_lower, int64_t ny_lower, int64_t sz_lower,
+                                const void* inp_upper, int64_t ny_upper, int64_t sz_upper, int64_t nx,
+                                int64_t ny, int64_t nz, int64_t sx, int64_t sy, int64_t sz, int dry_runs,
+                                double* time, void* stream) {
+  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sb200_hdiff_peer: domain must be positive");
+  if (sx != 1) return fail("sb200_hdiff_peer: only layout (2,1,0) is supported (unit stride along i)");
+  if ((inp_lower != nullptr && ny_lower < 2) || (inp_upper != nullptr && ny_upper < 2))
+    return fail("sb200_hdiff_peer: neighbouring slabs must hold at least two rows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const HdiffConfig cfg = hdiff_config();
+  bool used = false;
+  int rc = 0;
+  const bool aligned = aligned_to(inp, 16) && aligned_to(coeff, 16) && aligned_to(out, 16) &&
+                       (inp_lower == nullptr || aligned_to(inp_lower, 16)) &&
+                       (inp_upper == nullptr || aligned_to(inp_upper, 16));
+  if (!aligned) return fail("sb200_hdiff_peer: fields must be 16-byte aligned");
+  if (dtype == SB200_F64) {
+    if (sy % 2 || sz % 2 || sz_lower % 2 || sz_upper % 2)
+      return fail("sb200_hdiff_peer: strides must keep rows 16-byte aligned");
+    rc = launch_hdiff_tma<double>(static_cast<const double*>(inp), static_cast<const double*>(coeff),
+                                  static_cast<double*>(out), nx, ny, nz, sy, sz, cfg.jt, 0, dry_runs, time, s,
+                                  &used, static_cast<const double*>(inp_lower), ny_lower, sz_lower,
+                                  static_cast<const double*>(inp_upper), ny_upper, sz_upper);
+  } else if (dtype == SB200_F32) {
+    if (sy % 4 || sz % 4 || sz_lower % 4 || sz_upper % 4)
+      return fail("sb200_hdiff_peer: strides must keep rows 16-byte aligned");
+    rc = launch_hdiff_tma<float>(static_cast<const float*>(inp), static_cast<const float*>(coeff),
+                                 static_cast<float*>(out), nx, ny, nz, sy, sz, cfg.jt, 0, dry_runs, time, s,
+                                 &used, static_cast<const float*>(inp_lower), ny_lower, sz_lower,
+                                 static_cast<const float*>(inp_upper), ny_upper, sz_upper);
+  } else {
+    return fail("sb200_hdiff_peer: unsupported dtype");
+  }
+  if (rc == 0 && !used) return fail("sb200_hdiff_peer: the TMA path is not available for these fields");
+  return rc;
+}
 
 extern "C" int sb200_hdiff(int dtype, const void* inp, const void* coeff, void* out, int64_t nx,
                            int64_t ny, int64_t nz, int64_t sx, int64_t sy, int64_t sz,

@@ -190,6 +190,28 @@ int sb200_event_elapsed(void* start, void* stop, double* seconds) {
   return 0;
 }
 
+int sb200_ipc_get_handle(const void* dptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
+  if (handle64 == nullptr) return fail("sb200_ipc_get_handle: handle is NULL");
+  cudaIpcMemHandle_t handle;
+  SB200_CHECK(cudaIpcGetMemHandle(&handle, const_cast<void*>(dptr)));
+  std::memcpy(handle64, &handle, sizeof(handle));
+  return 0;
+}
+
+int sb200_ipc_open_handle(const void* handle64, void** dptr) {
+  if (handle64 == nullptr || dptr == nullptr) return fail("sb200_ipc_open_handle: NULL argument");
+  cudaIpcMemHandle_t handle;
+  std::memcpy(&handle, handle64, sizeof(handle));
+  SB200_CHECK(cudaIpcOpenMemHandle(dptr, handle, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int sb200_ipc_close_handle(void* dptr) {
+  SB200_CHECK(cudaIpcCloseMemHandle(dptr));
+  return 0;
+}
+
 int sb200_synchronize(void* stream) {
   if (stream == nullptr)
     SB200_CHECK(cudaDeviceSynchronize());

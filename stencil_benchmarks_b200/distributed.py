@@ -145,3 +145,47 @@ def cuda_halo_exchange(rank, world_size, dtype, nx, ny, nz, hx, sy, sz, width, g
                                   nx, nz, hx, sy, sz, j0, nrows, stream())
 
     return HaloExchange(dist, rank, world_size, ny, width, make_buffer, pack, unpack, group)
+
+
+class PeerSlabs:
+    """Neighbour slabs mapped into this process (CUDA IPC) for the fused halo exchange.
+
+    Every rank publishes the IPC handle of the device allocation that holds its ``inp`` field,
+    the offset of the first interior element inside it, its row count and its k stride; each rank opens the
+    handles of its lower / upper neighbour.  ``lower`` / ``upper`` are then device addresses of
+    the neighbours' first interior elements (or None), valid for TMA and ordinary loads over
+    NVLink.  ``sb200_hdiff_peer`` reads the halo rows through them inside the sweep itself.
+    """
+
+    def __init__(self, dist, rank, world_size, base_ptr, interior_ptr, ny, sz, group=None):
+        import ctypes
+
+        from . import capi
+
+        self._lib = capi.library()
+        handle = (ctypes.c_ubyte * 64)()
+        self._lib.sb200_ipc_get_handle(ctypes.c_void_p(base_ptr), handle)
+        mine = (bytes(handle), int(interior_ptr - base_ptr), int(ny), int(sz))
+        everyone = [None] * world_size
+        dist.all_gather_object(everyone, mine, group=group)
+        self._opened = []
+        self.lower = self.upper = None
+        self.ny_lower = self.ny_upper = 0
+        self.sz_lower = self.sz_upper = 0
+        lower, upper = neighbours(rank, world_size)
+        for who, neighbour in (("lower", lower), ("upper", upper)):
+            if neighbour is None:
+                continue
+            raw, offset, rows, kstride = everyone[neighbour]
+            mapped = ctypes.c_void_p()
+            self._lib.sb200_ipc_open_handle((ctypes.c_ubyte * 64).from_buffer_copy(raw),
+                                            ctypes.byref(mapped))
+            self._opened.append(mapped)
+            setattr(self, who, mapped.value + offset)
+            setattr(self, "ny_" + who, rows)
+            setattr(self, "sz_" + who, kstride)
+
+    def close(self):
+        for mapped in self._opened:
+            self._lib.sb200_ipc_close_handle(mapped)
+        self._opened = []

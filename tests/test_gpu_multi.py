@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, domain, results):
+def _worker(rank, world, port, domain, mode, results):
     import torch
     import torch.distributed as dist
 
@@ -53,13 +53,28 @@ def _worker(rank, world, port, domain, results):
         bench.upload(data, mirrors)
         ptr = {n: bench.interior_ptr(mirrors[n][1], h).value for n, h in zip(bench.args, data)}
         _, _, _, _, sy, sz = bench.geometry()
-        exchange = distributed.cuda_halo_exchange(rank, world, "float64", nx, ny, nz, 3, sy, sz, width=3)
-        requests = exchange.start(ptr["inp"])
-        exchange.finish(ptr["inp"], requests)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        capi.library().sb200_hdiff(capi.F64, ptr["inp"], ptr["coeff"], ptr["out"], nx, ny, nz, 1, sy, sz,
-                                   0, None, stream)
-        torch.cuda.synchronize()
+        if mode == "nccl":
+            exchange = distributed.cuda_halo_exchange(rank, world, "float64", nx, ny, nz, 3, sy, sz, width=3)
+            requests = exchange.start(ptr["inp"])
+            exchange.finish(ptr["inp"], requests)
+            capi.library().sb200_hdiff(capi.F64, ptr["inp"], ptr["coeff"], ptr["out"], nx, ny, nz, 1, sy, sz,
+                                       0, None, stream)
+            torch.cuda.synchronize()
+        else:
+            # fused exchange: the local halo rows keep their poison value, the sweep must read the
+            # neighbour's rows through peer memory instead
+            dist.barrier()
+            torch.cuda.synchronize()
+            peers = distributed.PeerSlabs(dist, rank, world, mirrors["inp"][0].ptr, ptr["inp"], ny, sz)
+            assert (peers.lower is not None) == (lower is not None)
+            assert (peers.upper is not None) == (upper is not None)
+            capi.library().sb200_hdiff_peer(capi.F64, ptr["inp"], ptr["coeff"], ptr["out"], peers.lower,
+                                            peers.ny_lower, peers.sz_lower, peers.upper, peers.ny_upper,
+                                            peers.sz_upper, nx, ny, nz, 1, sy, sz, 0, None, stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            peers.close()
         bench.download(data, mirrors)
         expected = stencils.hdiff(g_inp, g_coeff)
         ok = np.allclose(data.out[3:-3, 3:3 + ny, 3:-3], expected[3:-3, 3 + start:3 + start + ny, 3:-3],
@@ -69,12 +84,14 @@ def _worker(rank, world, port, domain, results):
         dist.destroy_process_group()
 
 
-def test_partitioned_hdiff_matches_global_oracle():
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+@pytest.mark.parametrize("domain", [(300, 64, 5), (512, 259, 3)])
+def test_partitioned_hdiff_matches_global_oracle(mode, domain):
     import torch
     import torch.multiprocessing as mp
 
     if capi.device_count() < 2:
         pytest.skip("needs two GPUs")
     results = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, _free_port(), (300, 64, 5), results), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), domain, mode, results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
