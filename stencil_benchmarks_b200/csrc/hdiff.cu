@@ -22,9 +22,9 @@
 // inp rows.  Every Laplacian / flux is computed once per thread; only the two
 // i-edge Laplacians and one i-edge flx are recomputed by the neighbouring
 // thread, which keeps the FP64 work at ~24 instructions per point (the
-// on-the-fly form needs ~46 and would be FP64-bound on B200).  No shared
-// memory, no barriers.  HBM traffic is the algorithmic minimum: inp halo
-// columns/rows are L1/L2 hits on lines a neighbouring thread or block fetched.
+// on-the-fly form needs ~46 and would be FP64-bound on B200).  The march needs
+// no block-wide barrier in either kernel.  HBM traffic is the algorithmic
+// minimum plus the 4 rows per march segment that two segments both read.
 #include <cstdlib>
 
 #include "common.cuh"

@@ -12,7 +12,9 @@ results are bit-identical to a single-GPU run of the global domain.
 STREAM, the basic copy and vertical advection need no exchange: vadv reads
 wcon(i+1, j) only, and i is not partitioned.
 
-The exchange is written against three injected callables (make_buffer, pack,
+Two exchanges exist for horizontal diffusion: ``PeerSlabs`` + ``sb200_hdiff_peer`` fuse it into
+the sweep (the edge tiles read the neighbours' rows over NVLink peer memory), ``HaloExchange``
+moves packed faces with send/recv.  The latter is written against three injected callables (make_buffer, pack,
 unpack) so the same neighbour / row arithmetic runs with CUDA kernels + NCCL in
 production (``cuda_halo_exchange``) and with NumPy + gloo in the CPU tests.
 """
