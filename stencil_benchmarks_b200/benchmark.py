@@ -46,6 +46,17 @@ except ImportError:
     class ExecutionError(RuntimeError):
         pass
 
+    def _infer(default):
+        """(element type, arity) implied by a default value."""
+        many = isinstance(default, (tuple, list))
+        values = list(default) if many else [default]
+        if not values:
+            raise ValueError("can not use empty tuple as default")
+        kinds = {type(v) for v in values}
+        if len(kinds) != 1:
+            raise ValueError("different types in default tuple")
+        return kinds.pop(), (len(values) if many else 1)
+
     class Parameter:
         """Typed, documented benchmark option (becomes a CLI flag in ``sbench``)."""
 
@@ -54,49 +65,38 @@ except ImportError:
                 if dtype is None or nargs is None:
                     raise ValueError("dtype and nargs must be given if default is None")
             else:
-                values = list(default) if isinstance(default, (tuple, list)) else [default]
-                if not values:
-                    raise ValueError("can not use empty tuple as default")
-                kinds = {type(v) for v in values}
-                if len(kinds) != 1:
-                    raise ValueError("different types in default tuple")
-                inferred_dtype = kinds.pop()
-                inferred_nargs = len(values) if isinstance(default, (tuple, list)) else 1
-                if dtype is None:
-                    dtype = inferred_dtype
-                elif dtype is not inferred_dtype:
+                implied_dtype, implied_nargs = _infer(default)
+                if dtype not in (None, implied_dtype):
                     raise ValueError("iconsistent default and dtype values")
-                if nargs is None:
-                    nargs = inferred_nargs
-                elif nargs != inferred_nargs:
+                if nargs not in (None, implied_nargs):
                     raise ValueError("inconsistent default and nargs values")
-            self.description = description
-            self.default = default
-            self.dtype = dtype
-            self.nargs = nargs
+                dtype, nargs = implied_dtype, implied_nargs
+            self.description, self.default = description, default
+            self.dtype, self.nargs = dtype, nargs
             self.choices = None if choices is None else tuple(choices)
 
-        def validate(self, value):
-            if value is None:
-                if self.default is None:
-                    raise ParameterError("value is required")
-                value = self.default
+        def _typed(self, value):
             if self.nargs == 1:
-                if not isinstance(value, self.dtype):
-                    raise ParameterError(
-                        f'wrong type of argument "{value}", '
-                        f' expected one of type "{self.dtype.__name__}"'
-                    )
-            else:
-                if not isinstance(value, (tuple, list)):
-                    raise ParameterError(
-                        f"{self.nargs} arguments of type "
-                        f'"{self.dtype.__name__}" required, found "{value}"'
-                    )
-                if len(value) != self.nargs:
-                    raise ParameterError(f'wrong number of arguments in argument "{value}"')
-                if not all(isinstance(v, self.dtype) for v in value):
-                    raise ParameterError(f'wrong type in argument "{value}"')
+                if isinstance(value, self.dtype):
+                    return
+                raise ParameterError(
+                    f'wrong type of argument "{value}", '
+                    f' expected one of type "{self.dtype.__name__}"')
+            if not isinstance(value, (tuple, list)):
+                raise ParameterError(
+                    f'{self.nargs} arguments of type "{self.dtype.__name__}" required, found "{value}"')
+            if len(value) != self.nargs:
+                raise ParameterError(f'wrong number of arguments in argument "{value}"')
+            if any(not isinstance(v, self.dtype) for v in value):
+                raise ParameterError(f'wrong type in argument "{value}"')
+
+        def validate(self, value):
+            """The value to use for `value` (None selects the default); raises ParameterError."""
+            if value is None:
+                value = self.default
+                if value is None:
+                    raise ParameterError("value is required")
+            self._typed(value)
             if self.choices is not None and value not in self.choices:
                 listed = ", ".join(f'"{c}"' for c in self.choices)
                 raise ParameterError(f'unsupported argument value "{value}", choices are {listed}')
@@ -109,12 +109,8 @@ except ImportError:
             )
 
         def __eq__(self, other):
-            return (
-                self.description == other.description
-                and self.dtype is other.dtype
-                and self.nargs == other.nargs
-                and self.default == other.default
-            )
+            mine = (self.description, self.dtype, self.nargs, self.default)
+            return mine == (other.description, other.dtype, other.nargs, other.default)
 
         __hash__ = None
 

@@ -23,60 +23,57 @@ from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import (
 )
 
 
-@click.group()
-def main():
-    pass
-
-
-common_kwargs = default_kwargs(verify=False, dry_runs=1, alignment=128, dtype="float64")
-
-
 def domains(k=80):
     for exponent in range(5, 12):
         yield 2**exponent, 2**exponent, k
 
 
-@main.command()
-@click.argument("output", type=click.Path())
-@click.option("--executions", "-e", type=int, default=101)
-@click.option("--option", "-o", multiple=True)
-def basic_bandwidth(output, executions, option):
-    kwargs = common_kwargs(option, halo=(1, 1, 1))
-    configurations = [
-        Configuration(basic.Empty, name="empty", **kwargs),
-        Configuration(basic.Copy, name="copy", **kwargs),
-        Configuration(basic.OnesidedAverage, name="avg-i", axis=0, **kwargs),
-        Configuration(basic.OnesidedAverage, name="avg-j", axis=1, **kwargs),
-        Configuration(basic.OnesidedAverage, name="avg-k", axis=2, **kwargs),
-        Configuration(basic.SymmetricAverage, name="sym-avg-i", axis=0, **kwargs),
-        Configuration(basic.SymmetricAverage, name="sym-avg-j", axis=1, **kwargs),
-        Configuration(basic.SymmetricAverage, name="sym-avg-k", axis=2, **kwargs),
-        Configuration(basic.Laplacian, name="lap-ij", along_x=True, along_y=True, along_z=False, **kwargs),
-    ]
-    run_scaling_benchmark(configurations, executions, domain_range=domains()).to_csv(output)
+common = default_kwargs(verify=False, dry_runs=1, alignment=128, dtype="float64")
+
+# family -> (levels k, extra keyword arguments, [(name, class, class arguments), ...])
+FAMILIES = {
+    "basic-bandwidth": (80, dict(halo=(1, 1, 1)), [
+        ("empty", basic.Empty, {}),
+        ("copy", basic.Copy, {}),
+        ("avg-i", basic.OnesidedAverage, dict(axis=0)),
+        ("avg-j", basic.OnesidedAverage, dict(axis=1)),
+        ("avg-k", basic.OnesidedAverage, dict(axis=2)),
+        ("sym-avg-i", basic.SymmetricAverage, dict(axis=0)),
+        ("sym-avg-j", basic.SymmetricAverage, dict(axis=1)),
+        ("sym-avg-k", basic.SymmetricAverage, dict(axis=2)),
+        ("lap-ij", basic.Laplacian, dict(along_x=True, along_y=True, along_z=False)),
+    ]),
+    "horizontal-diffusion-bandwidth": (80, {}, [("fused", hdiff.Fused, {})]),
+    "vertical-advection-bandwidth": (160, {}, [
+        ("thomas-onchip", vadv.Thomas, dict(coefficients="auto")),
+        ("thomas-global", vadv.Thomas, dict(coefficients="global")),
+    ]),
+}
 
 
-@main.command()
-@click.argument("output", type=click.Path())
-@click.option("--executions", "-e", type=int, default=101)
-@click.option("--option", "-o", multiple=True)
-def horizontal_diffusion_bandwidth(output, executions, option):
-    kwargs = common_kwargs(option)
-    configurations = [Configuration(hdiff.Fused, name="fused", **kwargs)]
-    run_scaling_benchmark(configurations, executions, domain_range=domains()).to_csv(output)
+@click.group()
+def main():
+    pass
 
 
-@main.command()
-@click.argument("output", type=click.Path())
-@click.option("--executions", "-e", type=int, default=101)
-@click.option("--option", "-o", multiple=True)
-def vertical_advection_bandwidth(output, executions, option):
-    kwargs = common_kwargs(option)
-    configurations = [
-        Configuration(vadv.Thomas, name="thomas-onchip", coefficients="auto", **kwargs),
-        Configuration(vadv.Thomas, name="thomas-global", coefficients="global", **kwargs),
-    ]
-    run_scaling_benchmark(configurations, executions, domain_range=domains(k=160)).to_csv(output)
+def _family_command(family):
+    levels, extra, members = FAMILIES[family]
+
+    @main.command(name=family)
+    @click.argument("output", type=click.Path())
+    @click.option("--executions", "-e", type=int, default=101)
+    @click.option("--option", "-o", multiple=True)
+    def command(output, executions, option):
+        kwargs = common(option, **extra)
+        configurations = [Configuration(cls, name=name, **cls_kwargs, **kwargs)
+                          for name, cls, cls_kwargs in members]
+        run_scaling_benchmark(configurations, executions, domain_range=domains(levels)).to_csv(output)
+
+    return command
+
+
+for _family in FAMILIES:
+    _family_command(_family)
 
 
 if __name__ == "__main__":
