@@ -318,61 +318,48 @@ __device__ __forceinline__ void rescale(float& p, float& r, float& q) {
 //     d[k] = (d0 - d[k-1] a) / (b - c[k-1] a)  =>  r' = d0 q - a r
 // so the level-to-level dependency is two FMAs instead of a division; the division needed to
 // store c[k], d[k] is off the critical path and pipelines across levels.
+//
+// With bet_m = bet_p = 1/2 the coefficients collapse onto h[k] = wsum[k] / 8 (exactly the oracle's
+// 0.25 * wsum * 0.5): a = as = -h[k], cc = cs = h[k+1], b = dtr + h[k] - h[k+1], and with
+// t[k] = h[k+1] * (stage[k+1] - stage[k]) the correction term is -t[k-1] - t[k].  Level 0 is the
+// same formula with h[0] := 0, t[-1] := 0 and (p, r, q) = (0, 0, 1); wcon[0] is never used.
 template <class T>
 struct VadvForward {
-  T wsum_cur = 0, wsum_next = 0, st_prev = 0, st_cur = 0, st_next = 0;
+  T h_cur = 0, h_next = 0, st_cur = 0, t_prev = 0;
   T pos_cur = 0, tens_cur = 0, tss_cur = 0;
   T p = 0, r = 0, q = 1;
 };
 
 // One lock-step iteration: level s of the new column has arrived (values v_*), level k = s-1 is
-// eliminated and stored in slot `slot`, after the old column's level nz-1-s has been
-// back-substituted from the same slot.  FIRST: s may be 0 or 1 (resolved at compile time in the
-// peeled first chunk).
+// eliminated and stored, after the old column's level nz-1-s has been back-substituted from the
+// same slot.  FIRST: s may be 0 (resolved at compile time in the peeled first chunk).
 template <class T, bool FIRST, int KIND>
 __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T v_pos, T v_tens,
                                           T v_tss, T v_wsum, T& z, const VadvCursor<T, KIND>& slot, int r,
                                           T* old_out, bool old_valid) {
-  using C = VadvConst<T>;
-  const T dtr_stage = C::dtr_stage, bet_m = C::bet_m, bet_p = C::bet_p;
-  f.wsum_cur = f.wsum_next;
-  f.wsum_next = v_wsum;
-  f.st_prev = f.st_cur;
-  f.st_cur = f.st_next;
-  f.st_next = v_stage;
+  const T dtr_stage = VadvConst<T>::dtr_stage;
   if (FIRST && s == 0) {
+    f.h_next = 0;
+    f.t_prev = 0;
+    f.p = 0; f.r = 0; f.q = 1;
+    f.st_cur = v_stage;
     f.pos_cur = v_pos; f.tens_cur = v_tens; f.tss_cur = v_tss;
     return;
   }
-  T pn, rn, qn;
-  if (FIRST && s == 1) {
-    // level 0 (base.py:417-429): c = cc / b, d = d0 / b
-    const T gcv = T(0.25) * f.wsum_next;
-    const T cs = gcv * bet_m;
-    const T cc = gcv * bet_p;
-    const T b = dtr_stage - cc;
-    const T correction = -cs * (f.st_next - f.st_cur);
-    const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur + correction;
-    pn = cc; rn = d0; qn = b;
-  } else {
-    const T gav = T(-0.25) * f.wsum_cur;
-    const T gcv = T(0.25) * f.wsum_next;
-    const T as = gav * bet_m;
-    const T cs = gcv * bet_m;
-    const T a = gav * bet_p;
-    const T cc = gcv * bet_p;
-    const T b = dtr_stage - a - cc;
-    const T correction = -as * (f.st_prev - f.st_cur) - cs * (f.st_next - f.st_cur);
-    const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur + correction;
-    pn = cc * f.q;
-    qn = b * f.q - a * f.p;
-    rn = d0 * f.q - a * f.r;
-  }
+  f.h_cur = f.h_next;
+  f.h_next = T(0.125) * v_wsum;
+  const T t = f.h_next * (v_stage - f.st_cur);
+  f.st_cur = v_stage;
+  const T b = dtr_stage + f.h_cur - f.h_next;
+  const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur - f.t_prev - t;
+  f.t_prev = t;
+  const T pn = f.h_next * f.q;
+  const T qn = b * f.q + f.h_cur * f.p;
+  const T rn = d0 * f.q + f.h_cur * f.r;
   f.p = pn; f.r = rn; f.q = qn;
   const T rq = fast_rcp(qn);
   const T c = pn * rq;
-  const T d = rn * rq;
-  const T e = d - f.pos_cur - c * v_pos;  // folded right-hand side of level s-1
+  const T e = rq * (rn - pn * v_pos) - f.pos_cur;  // d - pos[k] - c * pos[k+1], folded
   // backward step of the old column on the slot that is about to be overwritten
   T c_old, e_old;
   slot.load(r, c_old, e_old);
@@ -381,6 +368,7 @@ __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T
   slot.store(r, c, e);
   f.pos_cur = v_pos; f.tens_cur = v_tens; f.tss_cur = v_tss;
 }
+
 
 template <class T, int KD>
 __global__ void __launch_bounds__(vcfg::kThreads, 1)
@@ -467,7 +455,7 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
   } else {
     // ===== compute warps =====
     const int t = threadIdx.x;
-    const T dtr_stage = C::dtr_stage, bet_m = C::bet_m, bet_p = C::bet_p;
+    const T dtr_stage = C::dtr_stage;
     const VadvSlots<T> slots{*tmem_base_smem + (uint32_t(warp * 32) << 16), estore + t, paired};
 
     VadvForward<T> f;
@@ -545,13 +533,14 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
           VadvCursor<T, KIND> slot(slots, pa, dp);
           // output pointer of the old column: float64 schedules best when it is recomputed per
           // level, float32 (issue bound) when it is carried (measured, profiles/vadv_tuning_r01.log)
+          constexpr bool kRecompute = sizeof(T) == 8;
           T* out = old_base + int64_t(nz - 1 - s0) * sz;
 #pragma unroll
           for (int r = 0; r < KD; ++r) {
-            if (sizeof(T) == 8) out = old_base + int64_t(nz - 1 - (s0 + r)) * sz;
+            if (kRecompute) out = old_base + int64_t(nz - 1 - (s0 + r)) * sz;
             vadv_step<T, false, KIND>(s0 + r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
                                       slot, r, out, old_valid);
-            if (sizeof(T) == 4) out -= sz;
+            if (!kRecompute) out -= sz;
           }
         };
         if (kind == 1)
@@ -578,13 +567,10 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
       // ---- step nz: last level k = nz-1 of the new column (base.py:451-462) starts its
       //      backward sweep; the old column finished at step nz-1 ----
       {
-        const T gav = T(-0.25) * f.wsum_next;
-        const T as = gav * bet_m;
-        const T a = gav * bet_p;
-        const T bb = dtr_stage - a;
-        const T correction = -as * (f.st_cur - f.st_next);
-        const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur + correction;
-        const T x_top = (d0 * f.q - a * f.r) / (bb * f.q - a * f.p);
+        const T h = f.h_next;  // a = as = -h[nz-1], no c on the last level
+        const T bb = dtr_stage + h;
+        const T d0 = dtr_stage * f.pos_cur + f.tens_cur + f.tss_cur - f.t_prev;
+        const T x_top = (d0 * f.q + h * f.r) / (bb * f.q + h * f.p);
         z = x_top - f.pos_cur;
         if (new_valid) new_base[int64_t(nz - 1) * sz] = dtr_stage * z;
       }
