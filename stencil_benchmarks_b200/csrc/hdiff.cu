@@ -401,22 +401,22 @@ struct HdiffConfig {
   int variant = 0;
   int jt = 0;
   int hint_mode = 0;
+  int pipeline = 0;
 };
 
 inline HdiffConfig hdiff_config() {
   HdiffConfig cfg;
   if (const char* env = std::getenv("SB200_HDIFF_CFG"))
-    std::sscanf(env, "%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode);
+    std::sscanf(env, "%d,%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode, &cfg.pipeline);
   return cfg;
 }
 
-template <class T>
-int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
+template <class T, int R, int S>
+int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
                      int64_t sy, int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
                      cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
                      int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
                      int64_t sz_upper = 0) {
-  constexpr int R = 4, S = 3;
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
   constexpr int E = 8 / int(sizeof(T));  // data elements per 8-byte TMA element
@@ -493,6 +493,26 @@ int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t n
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);
+}
+
+// rows per stage x stages of the TMA ring; SB200_HDIFF_CFG fourth field selects an alternative
+template <class T>
+int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz, int64_t sy,
+                     int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
+                     cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
+                     int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
+                     int64_t sz_upper = 0) {
+#define SB200_TMA_ARGS                                                                              \
+  inp, coeff, out, nx, ny, nz, sy, sz, jt_request, hint_mode, dry_runs, time, stream, used, inp_lower, \
+      ny_lower, sz_lower, inp_upper, ny_upper, sz_upper
+  switch (hdiff_config().pipeline) {
+    case 1: return launch_hdiff_tma_rs<T, 4, 3>(SB200_TMA_ARGS);
+    case 2: return launch_hdiff_tma_rs<T, 8, 2>(SB200_TMA_ARGS);
+    case 3: return launch_hdiff_tma_rs<T, 8, 3>(SB200_TMA_ARGS);
+    case 4: return launch_hdiff_tma_rs<T, 2, 6>(SB200_TMA_ARGS);
+    default: return launch_hdiff_tma_rs<T, 4, 4>(SB200_TMA_ARGS);  // best of the sweep, by <1 %
+  }
+#undef SB200_TMA_ARGS
 }
 
 template <class T>
