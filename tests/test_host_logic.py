@@ -181,3 +181,36 @@ def test_fields_alloc_and_nbytes():
         fields.alloc_array((2, 3), "int32", (0, 0))
     assert cabi.data_ptr(z, (1, 1, 1)).value == z.ctypes.data + 8 + z.strides[1] + z.strides[2]
     assert cabi.dtype_cname("float64") == "double" and cabi.dtype_cname("int16") == "std::int16_t"
+
+
+def test_missing_library_is_a_parameter_error(monkeypatch, tmp_path):
+    """No library, no benchmark: like a failed compilation in the reference (cuda_hip/mixin.py:79-84)."""
+    capi.library.cache_clear()
+    monkeypatch.setattr(capi, "LIBRARY_PATH", tmp_path / "libsbench_b200.so")
+    try:
+        with pytest.raises(benchmark.ParameterError, match="does not exist"):
+            horizontal_diffusion.Fused(domain=(8, 8, 4), **CPU)
+        with pytest.raises(benchmark.ParameterError, match="does not exist"):
+            stream.Native(array_size=1024)
+    finally:
+        monkeypatch.undo()
+        capi.library.cache_clear()
+        capi.library()
+
+
+def test_bench_accounting_and_config():
+    import importlib.util
+    import pathlib
+
+    spec = importlib.util.spec_from_file_location("bench", pathlib.Path(__file__).parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.algorithmic_bytes("hdiff", (2048, 2048, 80)) == 8063559680
+    assert bench.algorithmic_bytes("vadv", (1024, 1024, 160)) == 8053063680
+    assert bench.algorithmic_bytes("triad", None) == 3 * 8 * (1 << 30)
+    cfg = bench.workload_config("hdiff", 8, "peer")
+    assert cfg["global_domain"] == [2048, 16384, 80] and "peer memory" in cfg["halo_exchange"]
+    assert bench.workload_config("hdiff", 1, "peer")["halo_exchange"] == "none"
+    assert "NCCL" in bench.workload_config("hdiff", 2, "nccl")["halo_exchange"]
+    peak, source = bench.measured_peak()
+    assert peak > 1000 and ("measured" in source or "fallback" in source)
