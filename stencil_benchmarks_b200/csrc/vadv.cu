@@ -144,21 +144,43 @@ __global__ void __launch_bounds__(128)
 // HBM traffic = 5 reads + 1 write per point; storage limits: (nz-1) * 128 * sizeof(T) bytes of
 // shared memory next to the ring, (nz-1) * sizeof(T)/4 <= 512 TMEM columns.
 namespace vcfg {
-constexpr int kCols = 128;
-constexpr int kThreads = kCols + 32;
+// Columns per batch = compute threads per CTA.  float64: 128 (4 warps, one per scheduler; the
+// per-column store of a 160-level column fills TMEM + shared memory).  float32 values are half
+// the size, so 256 columns fit: 8 warps, two per scheduler, which hides the per-level issue
+// latency that bounds the float64 kernel.  Two warps on one scheduler share a TMEM lane quarter
+// and split its 512 columns.
+template <class T>
+__host__ __device__ constexpr int cols() { return sizeof(T) == 8 ? 128 : 256; }
+template <class T>
+__host__ __device__ constexpr int threads() { return cols<T>() + 32; }
 constexpr int kTmemCols = 512;
-// ring stage = 4 tiles of KD x 128 values + 2 wcon tiles of KD x (128 + 16 B) values, the
-// latter padded to 128 bytes so every TMA destination stays 128-byte aligned
 template <class T>
-__host__ __device__ constexpr int wcon_width() { return kCols + 16 / int(sizeof(T)); }
+__host__ __device__ constexpr int tmem_cols_per_thread() { return kTmemCols / (cols<T>() / 128); }
+// ring stage = 4 tiles of KD x cols values + 2 wcon tiles.  A wcon tile carries 16 more bytes per
+// level (wcon(i+1) of the last column): inside the box where the box stays <= 256 elements
+// (float64), as a second, 16-byte wide box otherwise (float32).  Tiles are padded to 128 bytes so
+// every TMA destination stays 128-byte aligned.
 template <class T>
-__host__ __device__ constexpr int tile_bytes(int kd) { return kd * kCols * int(sizeof(T)); }
+__host__ __device__ constexpr int edge_elems() { return 16 / int(sizeof(T)); }
+template <class T>
+__host__ __device__ constexpr bool split_wcon() { return cols<T>() + edge_elems<T>() > 256; }
+template <class T>
+__host__ __device__ constexpr int wcon_width() { return split_wcon<T>() ? cols<T>() : cols<T>() + edge_elems<T>(); }
+template <class T>
+__host__ __device__ constexpr int tile_bytes(int kd) { return kd * cols<T>() * int(sizeof(T)); }
 template <class T>
 __host__ __device__ constexpr int wcon_bytes(int kd) { return kd * wcon_width<T>() * int(sizeof(T)); }
 template <class T>
-__host__ __device__ constexpr int wcon_tile_bytes(int kd) { return (wcon_bytes<T>(kd) + 127) / 128 * 128; }
+__host__ __device__ constexpr int wcon_main_bytes(int kd) { return (wcon_bytes<T>(kd) + 127) / 128 * 128; }
 template <class T>
-__host__ __device__ constexpr int stage_bytes(int kd) { return 4 * tile_bytes<T>(kd) + 2 * wcon_tile_bytes<T>(kd); }
+__host__ __device__ constexpr int wcon_edge_bytes(int kd) { return split_wcon<T>() ? (kd * 16 + 127) / 128 * 128 : 0; }
+template <class T>
+__host__ __device__ constexpr int wcon_tile_bytes(int kd) { return wcon_main_bytes<T>(kd) + wcon_edge_bytes<T>(kd); }
+// bytes TMA delivers for one wcon tile with (first tile) / without (j+1 tile) the i+1 edge
+template <class T>
+__host__ __device__ constexpr int wcon_tx_bytes(int kd, bool with_edge) {
+  return wcon_bytes<T>(kd) + (split_wcon<T>() && with_edge ? kd * 16 : 0);
+}
 }  // namespace vcfg
 
 __device__ __forceinline__ void tmem_store(uint32_t taddr, double v) {
@@ -221,7 +243,7 @@ template <class T>
 struct VadvSlots {
   static constexpr int TCOLS = int(sizeof(T)) / 4;
   uint32_t tmem;  // TMEM address of this warp's lane quarter, column 0 of the allocation
-  T* smem;        // this thread's column of the shared-memory part: slot q at smem[q * kCols]
+  T* smem;        // this thread's column of the shared-memory part: slot q at smem[q * cols]
   int paired;
 
   // KIND: 0 = slot known to be split, 1 = known to be paired, 2 = decide at run time
@@ -231,7 +253,7 @@ struct VadvSlots {
       tmem_load_pair(tmem + uint32_t(2 * TCOLS * p), c, e);
     } else {
       tmem_load(tmem + uint32_t(2 * TCOLS * paired + TCOLS * (p - paired)), c);
-      e = smem[(p - paired) * vcfg::kCols];
+      e = smem[(p - paired) * vcfg::cols<T>()];
     }
   }
   template <int KIND>
@@ -240,7 +262,7 @@ struct VadvSlots {
       tmem_store_pair(tmem + uint32_t(2 * TCOLS * p), c, e);
     } else {
       tmem_store(tmem + uint32_t(2 * TCOLS * paired + TCOLS * (p - paired)), c);
-      smem[(p - paired) * vcfg::kCols] = e;
+      smem[(p - paired) * vcfg::cols<T>()] = e;
     }
   }
 };
@@ -259,7 +281,7 @@ struct VadvCursor {
     return KIND == 1 ? uint32_t(2 * TCOLS * q) : uint32_t(2 * TCOLS * slots.paired + TCOLS * (q - slots.paired));
   }
   __device__ __forceinline__ T* shared(int r) const {
-    return slots.smem + (p + r * dp - slots.paired) * vcfg::kCols;
+    return slots.smem + (p + r * dp - slots.paired) * vcfg::cols<T>();
   }
   __device__ __forceinline__ void load(int r, T& c, T& e) const {
     if (KIND == 1) {
@@ -371,16 +393,20 @@ __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T
 
 
 template <class T, int KD>
-__global__ void __launch_bounds__(vcfg::kThreads, 1)
+__global__ void __launch_bounds__(vcfg::threads<T>(), 1)
     vadv_onchip_kernel(const __grid_constant__ CUtensorMap map_stage,
                        const __grid_constant__ CUtensorMap map_pos,
                        const __grid_constant__ CUtensorMap map_tens,
                        const __grid_constant__ CUtensorMap map_tensstage,
-                       const __grid_constant__ CUtensorMap map_wcon, T* __restrict__ tensstage,
+                       const __grid_constant__ CUtensorMap map_wcon,
+                       const __grid_constant__ CUtensorMap map_wcon_edge, T* __restrict__ tensstage,
                        int nx, int ny, int nz, int64_t sy, int64_t sz, int ishift, int jshift,
                        int stages, int paired) {
   using C = VadvConst<T>;
-  constexpr int COLS = vcfg::kCols;
+  constexpr int COLS = vcfg::cols<T>();
+  constexpr bool SPLIT = vcfg::split_wcon<T>();
+  constexpr int EDGE = vcfg::edge_elems<T>();
+  constexpr int WMAIN = vcfg::wcon_main_bytes<T>(KD);
   constexpr int TILE = vcfg::tile_bytes<T>(KD);           // one field, KD levels
   constexpr int WB = vcfg::wcon_width<T>();                // wcon tile width in elements
   constexpr int WTILE = vcfg::wcon_tile_bytes<T>(KD);
@@ -427,7 +453,9 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
       tma::prefetch_tensormap(&map_tens);
       tma::prefetch_tensormap(&map_tensstage);
       tma::prefetch_tensormap(&map_wcon);
-      const uint32_t tx_bytes = 4 * TILE + (jshift ? 2 : 1) * vcfg::wcon_bytes<T>(KD);
+      if (SPLIT) tma::prefetch_tensormap(&map_wcon_edge);
+      const uint32_t tx_bytes = 4 * TILE + vcfg::wcon_tx_bytes<T>(KD, true) +
+                                (jshift ? vcfg::wcon_tx_bytes<T>(KD, false) : 0);
       int slot = 0, round = 0;  // ring position of the running chunk counter
       for (int m = 0; m < my_batches; ++m) {
         const int b = int(blockIdx.x) + m * int(gridDim.x);
@@ -443,6 +471,7 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
           tma::load_3d(stage + 2 * TILE, &map_tens, it, j, k0, &full[slot]);
           tma::load_3d(stage + 3 * TILE, &map_tensstage, it, j, k0, &full[slot]);
           tma::load_3d(stage + 4 * TILE, &map_wcon, it, j, k0, &full[slot]);
+          if (SPLIT) tma::load_3d(stage + 4 * TILE + WMAIN, &map_wcon_edge, it + COLS, j, k0, &full[slot]);
           if (jshift) tma::load_3d(stage + 4 * TILE + WTILE, &map_wcon, it, j + 1, k0, &full[slot]);
           if (++slot == stages) {
             slot = 0;
@@ -456,7 +485,10 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
     // ===== compute warps =====
     const int t = threadIdx.x;
     const T dtr_stage = C::dtr_stage;
-    const VadvSlots<T> slots{*tmem_base_smem + (uint32_t(warp * 32) << 16), estore + t, paired};
+    // TMEM: lane quarter of the warp's scheduler; two warps on one scheduler split the columns
+    const VadvSlots<T> slots{*tmem_base_smem + (uint32_t((warp & 3) * 32) << 16) +
+                                 uint32_t((warp >> 2) * vcfg::tmem_cols_per_thread<T>()),
+                             estore + t, paired};
 
     VadvForward<T> f;
     T z = 0;                // backward state of the old column: x - pos of the level above
@@ -477,7 +509,15 @@ __global__ void __launch_bounds__(vcfg::kThreads, 1)
       // j+1 from the second tile
       const T* w0 = reinterpret_cast<const T*>(stage + 4 * TILE) + r * WB + t;
       const T* w1 = reinterpret_cast<const T*>(stage + 4 * TILE + WTILE) + r * WB + t;
-      v_wsum = (jshift ? w1[0] : w0[ishift]) + w0[0];
+      T shifted;
+      if (jshift) {
+        shifted = w1[0];
+      } else if (SPLIT && t + ishift >= COLS) {
+        shifted = reinterpret_cast<const T*>(stage + 4 * TILE + WMAIN)[r * EDGE];  // wcon(i+1) of the last column
+      } else {
+        shifted = w0[ishift];
+      }
+      v_wsum = shifted + w0[0];
     };
     auto release = [&]() {
       __syncwarp();
@@ -624,13 +664,14 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
                        int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz, int ishift,
                        int jshift, int dry_runs, double* time, cudaStream_t stream, bool* used) {
   constexpr int KD = 4;
-  constexpr int COLS = vcfg::kCols;
+  constexpr int COLS = vcfg::cols<T>();
   *used = false;
-  // TMEM: c of every slot, plus e of as many slots as the remaining columns hold
+  // TMEM: c of every slot, plus e of as many slots as the thread's remaining columns hold
   constexpr int TCOLS = int(sizeof(T)) / 4;
+  constexpr int BUDGET = vcfg::tmem_cols_per_thread<T>();
   const int64_t slots = nz - 1;
-  if (slots * TCOLS > vcfg::kTmemCols) return 0;
-  int paired = int(std::min<int64_t>(slots, (vcfg::kTmemCols - slots * TCOLS) / TCOLS));
+  if (slots * TCOLS > BUDGET) return 0;
+  int paired = int(std::min<int64_t>(slots, (BUDGET - slots * TCOLS) / TCOLS));
   if (const char* env = std::getenv("SB200_VADV_PAIRED")) paired = std::min(paired, std::atoi(env));
   int max_stages = 8;
   if (const char* env = std::getenv("SB200_VADV_STAGES")) max_stages = std::max(2, std::atoi(env));
@@ -642,12 +683,13 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
   const size_t smem = stages * stage_size + fixed;
   const auto type = tma::tensor_type<T>();
   const uint64_t s1 = uint64_t(sy) * sizeof(T), s2 = uint64_t(sz) * sizeof(T);
-  CUtensorMap m_stage, m_pos, m_tens, m_tss, m_wcon;
+  CUtensorMap m_stage, m_pos, m_tens, m_tss, m_wcon, m_wcon_edge;
   if (!tma::encode_3d(&m_stage, type, stage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
       !tma::encode_3d(&m_pos, type, pos, nx, ny, nz, s1, s2, COLS, 1, KD) ||
       !tma::encode_3d(&m_tens, type, tens, nx, ny, nz, s1, s2, COLS, 1, KD) ||
       !tma::encode_3d(&m_tss, type, tensstage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
-      !tma::encode_3d(&m_wcon, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::wcon_width<T>(), 1, KD))
+      !tma::encode_3d(&m_wcon, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::wcon_width<T>(), 1, KD) ||
+      !tma::encode_3d(&m_wcon_edge, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::edge_elems<T>(), 1, KD))
     return 0;
   // per launch: the attribute is per device, and a process may drive several devices
   SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD>,
@@ -656,8 +698,8 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
   const unsigned grid = unsigned(std::min<int64_t>(nbatches, sm_count()));
   *used = true;
   auto launch = [&] {
-    vadv_onchip_kernel<T, KD><<<grid, vcfg::kThreads, smem, stream>>>(
-        m_stage, m_pos, m_tens, m_tss, m_wcon, tensstage, int(nx), int(ny), int(nz), sy, sz, ishift, jshift,
+    vadv_onchip_kernel<T, KD><<<grid, vcfg::threads<T>(), smem, stream>>>(
+        m_stage, m_pos, m_tens, m_tss, m_wcon, m_wcon_edge, tensstage, int(nx), int(ny), int(nz), sy, sz, ishift, jshift,
         stages, paired);
     count_launch();
   };
