@@ -378,3 +378,26 @@ def test_basic_full_size_float32():
     native.laplacian(data.inp, expected, bench.halo, (True, True, False))
     inner = bench.inner_slice()
     assert close(data.out[inner], expected[inner], "float32")
+
+
+@pytest.mark.parametrize("all_components", [False, True])
+def test_vadv_float32_wide_batches(all_components):
+    """float32 runs 256-column batches (8 warps, split wcon box): several batches per row, the last
+    one partial, the i+1 neighbour of a batch's last column coming from the 16-byte edge box."""
+    halo = (1, 1, 1)
+    bench = vertical_advection.Thomas(domain=(600, 5, 40), halo=halo, dtype="float32", verify=False, seed=31,
+                                      all_components=all_components, coefficients="onchip")
+    before = snapshot(bench)
+    bench.run()
+    inner = bench.inner_slice()
+    shifts = {"u": (1, 0), "v": (0, 1), "w": (0, 0)}
+    for c in ("uvw" if all_components else "u"):
+        expected = stencils._vadv_component(
+            before[c + "stage"], before[c + "pos"], before[c + "tens"], before[c + "tensstage"],
+            before["wcon"], halo, *shifts[c])[inner]
+        out = getattr(bench.data(), c + "tensstage")[inner]
+        bad = ~np.isclose(out, expected, **stencils.tolerances("float32"))
+        assert bad.mean() < 1e-2, f"{c}: {bad.sum()} of {bad.size} points differ"
+        # the columns next to a batch border (i = 255, 256, 511, 512) must be as good as the rest
+        for i in (255, 256, 511, 512):
+            assert bad[i].mean() < 5e-2, f"{c}: column block i={i} differs"
