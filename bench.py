@@ -293,9 +293,24 @@ def run_b200(args):
     exchange = None
     peers = None
     if args.workload == "hdiff" and world > 1 and args.exchange == "peer":
-        # fused exchange: neighbours' inp slabs mapped through CUDA IPC, halo rows read by TMA
-        peers = distributed.PeerSlabs(dist, rank, world, mirrors["inp"][0].ptr, pointers["inp"].value, ny, sz)
-    elif args.workload == "hdiff" and world > 1:
+        # fused exchange: neighbours' inp slabs mapped through CUDA IPC, halo rows read by TMA.
+        # If any rank cannot map its neighbours (IPC disabled in the container), every rank
+        # switches to the NCCL exchange -- still a GPU path -- and the line says so.
+        try:
+            peers = distributed.PeerSlabs(dist, rank, world, mirrors["inp"][0].ptr, pointers["inp"].value,
+                                          ny, sz)
+            mapped = 1
+        except Exception as error:  # noqa: BLE001 - reported, not swallowed
+            print(f"rank {rank}: peer mapping failed ({error}); using the NCCL exchange", file=sys.stderr)
+            mapped = 0
+        flag = torch.tensor([mapped], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if peers is not None:
+                peers.close()
+                peers = None
+            args.exchange = "nccl"
+    if args.workload == "hdiff" and world > 1 and peers is None:
         exchange = distributed.cuda_halo_exchange(rank, world, cfg["dtype"], nx, ny, nz, cfg["halo"][0],
                                                   sy, sz, width=cfg["halo"][1])
         (lo, hi), strips = distributed.interior_and_boundary_rows(
