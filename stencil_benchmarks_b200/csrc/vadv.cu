@@ -122,27 +122,30 @@ __global__ void __launch_bounds__(128)
 // ---------------------------------------------------------------------------------
 // ONCHIP variant
 // ---------------------------------------------------------------------------------
-// Persistent CTAs (one per SM): 4 compute warps + 1 TMA producer warp.  A batch is 128
-// consecutive-i columns of one j row; thread t owns column i_t + t for all levels.
+// Persistent CTAs (one per SM): 4 compute warps (float32: 8) + 1 TMA producer warp.  A batch is
+// 128 (float32: 256) consecutive-i columns of one j row; thread t owns column i_t + t for all levels.
 //
-//  * Input levels arrive through a TMA ring (boxes of 128 columns x KD levels for ustage,
-//    upos, utens, utensstage; 128 + 16 bytes wide for wcon so that wcon(i+1) of the last
-//    column is in the tile -- TMA needs 16-byte aligned box origins, so the i+1 neighbour
+//  * Input levels arrive through a TMA ring (boxes of one batch x KD levels for ustage, upos,
+//    utens, utensstage and wcon; the wcon tile carries 16 more bytes per level so that wcon(i+1)
+//    of the last column is there -- TMA needs 16-byte aligned box origins, so the i+1 neighbour
 //    cannot be a second, shifted box; the j+1 neighbour of the v component can), so the
-//    k-sequential compute never waits on a global load it issued itself and ~60 KB per SM
-//    are in flight.
-//  * The Thomas coefficients of a column are private to its thread: c[k] is parked in TMEM
-//    (tcgen05.st/ld, lane = thread, two 32-bit columns per double), and the right-hand side in
-//    shared memory, already folded for the backward sweep:
+//    k-sequential compute never waits on a global load it issued itself.  Up to 8 stages of
+//    4 levels are in flight (~160 KB per SM).
+//  * The Thomas coefficients of a column are private to its thread and live on chip: c[k] of
+//    every level in TMEM (tcgen05.st/ld, lane = thread), next to it the right-hand side of as
+//    many levels as the thread's TMEM columns hold, the remaining right-hand sides in shared
+//    memory.  The right-hand side is stored folded for the backward sweep:
 //        e[k] = d[k] - pos[k] - c[k]*pos[k+1]   =>   z[k] = x[k] - pos[k] = e[k] - c[k]*z[k+1],
 //        utensstage[k] = dtr * z[k]
 //    so the backward sweep reads nothing from HBM.
 //  * The backward sweep of batch n runs in lock-step with the forward sweep of batch n+1:
 //    at step s the thread consumes slot p of the old column (level nz-1-s) and then stores the
 //    new column's level s-1 into the same slot.  One set of nz-1 slots per thread suffices and
-//    the two dependency chains (forward with its division, backward FMA) overlap.
-// HBM traffic = 5 reads + 1 write per point; storage limits: (nz-1) * 128 * sizeof(T) bytes of
-// shared memory next to the ring, (nz-1) * sizeof(T)/4 <= 512 TMEM columns.
+//    the two dependency chains (forward recurrence, backward FMA) overlap.
+//  * The forward recurrence is division free (homogeneous triple p, r, q; see VadvForward).
+// HBM traffic = 5 reads + 1 write per point.  Storage limits: (nz-1) * sizeof(T)/4 TMEM columns
+// per thread (512, or 256 where two warps share a lane quarter) and shared memory for the
+// right-hand sides that do not fit TMEM next to at least two ring stages.
 namespace vcfg {
 // Columns per batch = compute threads per CTA.  float64: 128 (4 warps, one per scheduler; the
 // per-column store of a 160-level column fills TMEM + shared memory).  float32 values are half
