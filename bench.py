@@ -532,12 +532,6 @@ def run_triad(args):
     return 0
 
 
-def capi_nbytes(host):
-    from stencil_benchmarks_b200.tools import fields
-
-    return fields.nbytes(host)
-
-
 def extra_kernels(lib, capi, args):
     """Device-timed STREAM triad (2^28 f64; 2^30 with --full-stream) and the other stencil."""
     import numpy as np
