@@ -524,8 +524,9 @@ int launch_hdiff(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, i
   // vector paths: 16-byte aligned interior origin and strides that keep every row aligned
   const bool vector_ok = aligned_to(inp, 16) && aligned_to(coeff, 16) && aligned_to(out, 16) &&
                          sy % V == 0 && sz % V == 0;
-  // TMA path: worth it once a 2 KB tile is at least half full
-  if (vector_ok && cfg.variant != 1 && (cfg.variant == 2 || nx * int64_t(sizeof(T)) >= 1024)) {
+  // TMA path: faster than the generic march even when the 2 KB tile is only a quarter full
+  // (profiles/size_sweep_r01.log)
+  if (vector_ok && cfg.variant != 1 && (cfg.variant == 2 || nx * int64_t(sizeof(T)) >= 512)) {
     bool used = false;
     const int rc = launch_hdiff_tma<T>(inp, coeff, out, nx, ny, nz, sy, sz, cfg.jt, cfg.hint_mode, dry_runs,
                                        time, stream, &used);
@@ -536,11 +537,19 @@ int launch_hdiff(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, i
   int bx = 128;
   while (bx > 32 && bx / 2 >= nvec) bx /= 2;
   const dim3 block(bx, 1, 1);
-  const dim3 grid(unsigned(ceil_div(nvec, bx)), unsigned(ceil_div(ny, JT)), unsigned(nz));
+  // long marches amortise the 4 warm-up rows; small domains need short ones to fill the GPU
+  constexpr int JT_SHORT = 16;
+  const bool short_march = ceil_div(nvec, bx) * ceil_div(ny, JT) * nz < 148 * 8;
+  const int jt = short_march ? JT_SHORT : JT;
+  const dim3 grid(unsigned(ceil_div(nvec, bx)), unsigned(ceil_div(ny, jt)), unsigned(nz));
   if (grid.y > 65535u || grid.z > 65535u) return fail("sb200_hdiff: domain too large for the launch grid");
   auto launch = [&] {
-    if (vector_ok)
+    if (vector_ok && short_march)
+      hdiff_jmarch_kernel<T, V, JT_SHORT><<<grid, block, 0, stream>>>(inp, coeff, out, int(nx), int(ny), sy, sz);
+    else if (vector_ok)
       hdiff_jmarch_kernel<T, V, JT><<<grid, block, 0, stream>>>(inp, coeff, out, int(nx), int(ny), sy, sz);
+    else if (short_march)
+      hdiff_jmarch_kernel<T, 1, JT_SHORT><<<grid, block, 0, stream>>>(inp, coeff, out, int(nx), int(ny), sy, sz);
     else
       hdiff_jmarch_kernel<T, 1, JT><<<grid, block, 0, stream>>>(inp, coeff, out, int(nx), int(ny), sy, sz);
     count_launch();
