@@ -222,7 +222,17 @@ EXCHANGE_TEXT = {
 }
 
 
-def workload_config(workload, n_gpus, exchange=None):
+def local_domain(workload, n_gpus, rank, scaling):
+    """Domain one rank sweeps: the full BASELINE domain (weak) or its J slab of it (strong)."""
+    nx, ny, nz = WORKLOADS[workload]["domain"]
+    if scaling == "strong" and n_gpus > 1:
+        from stencil_benchmarks_b200 import distributed
+
+        ny = distributed.split_rows(ny, n_gpus)[rank][1]
+    return nx, ny, nz
+
+
+def workload_config(workload, n_gpus, exchange=None, scaling="weak"):
     if workload == "triad":
         return {
             "workload": f"STREAM triad a = b + 3c, {TRIAD_N} float64 elements per array per GPU",
@@ -232,13 +242,18 @@ def workload_config(workload, n_gpus, exchange=None):
         }
     cfg = WORKLOADS[workload]
     nx, ny, nz = cfg["domain"]
+    strong = scaling == "strong" and n_gpus > 1
+    per_gpu = local_domain(workload, n_gpus, 0, scaling)
+    resident_gb = (3 if workload == "hdiff" else 8) * (nx + 6) * (per_gpu[1] + 6) * (nz + 6) * 8 / 1e9
     return {
-        "workload": f"{workload} {nx}x{ny}x{nz} float64 per GPU, halo 3, alignment 128",
-        "global_domain": [nx, ny * n_gpus, nz],
+        "workload": (f"{workload} {nx}x{ny}x{nz} float64 " + ("global" if strong else "per GPU")
+                     + ", halo 3, alignment 128"),
+        "global_domain": [nx, ny if strong else ny * n_gpus, nz],
+        "per_gpu_domain": list(per_gpu),
         "partition": "J slabs, one per GPU" if n_gpus > 1 else "single GPU",
         "halo_exchange": (EXCHANGE_TEXT.get(exchange, "none") if workload == "hdiff" and n_gpus > 1 else "none"),
-        "bytes_per_step_per_gpu": algorithmic_bytes(workload, cfg["domain"]),
-        "l2": "fields (8.7 GB hdiff / 11.3 GB vadv per GPU) exceed the 126 MB L2; no flush between steps",
+        "bytes_per_step_per_gpu": algorithmic_bytes(workload, per_gpu),
+        "l2": f"fields ({resident_gb:.1f} GB per GPU) exceed the 126 MB L2; no flush between steps",
     }
 
 
@@ -275,9 +290,10 @@ def run_b200(args):
 
     lib = capi.library()
     cfg = WORKLOADS[args.workload]
-    nx, ny, nz = cfg["domain"]
+    domain = local_domain(args.workload, world, rank, args.scaling)
+    nx, ny, nz = domain
     cls = horizontal_diffusion.Fused if args.workload == "hdiff" else vertical_advection.Thomas
-    bench = cls(domain=cfg["domain"], halo=cfg["halo"], dtype=cfg["dtype"], verify=False,
+    bench = cls(domain=domain, halo=cfg["halo"], dtype=cfg["dtype"], verify=False,
                 device=local_rank, seed=100 + rank, dry_runs=0)
     data = bench.data()
     mirrors = bench._device_fields(data)
@@ -372,8 +388,11 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    nbytes = algorithmic_bytes(args.workload, cfg["domain"])
-    value = world * nbytes / (ms_per_step * 1e-3) / 1e9
+    # bytes of one rank (rank 0's slab is the largest); whole job = every rank's slab
+    nbytes = algorithmic_bytes(args.workload, local_domain(args.workload, world, 0, args.scaling))
+    job_bytes = sum(algorithmic_bytes(args.workload, local_domain(args.workload, world, r, args.scaling))
+                    for r in range(world))
+    value = job_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end through the plugin API: H2D inputs + kernel + D2H outputs per step ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -390,15 +409,16 @@ def run_b200(args):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * nbytes / e2e_s / 1e9
+    e2e_value = job_bytes / e2e_s / 1e9
 
     peak, peak_source = measured_peak()
     achieved = nbytes / (ms_per_step * 1e-3) / 1e9
     line = {
         "metric": METRIC[args.workload], "value": value, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.workload, world, args.exchange),
+        "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.workload, world, args.exchange, args.scaling),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
                      "peak_source": peak_source,
@@ -561,6 +581,9 @@ def main():
     parser.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                         help="hdiff halo exchange at N > 1: fused into the sweep over peer memory, "
                              "or NCCL send/recv on a second stream")
+    parser.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                        help="weak: the BASELINE domain per GPU (default, what the driver measures); "
+                             "strong: the BASELINE domain split into J slabs over the GPUs")
     parser.add_argument("--e2e-steps", type=int, default=3)
     parser.add_argument("--e2e-chunks", type=int, default=8)
     parser.add_argument("--no-extras", action="store_true")

@@ -95,3 +95,88 @@ def test_partitioned_hdiff_matches_global_oracle(mode, domain):
     results = mp.Manager().dict()
     mp.spawn(_worker, args=(2, _free_port(), domain, mode, results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def _global_rows(field_seed, rows, nx, nz):
+    """Rows [rows) of a global (nx+6, ny+6, nz+6) field whose j-th row depends on (seed, j) only,
+    so every rank can build its slab -- and the true halo rows around it -- without the whole field."""
+    out = np.empty((nx + 6, len(rows), nz + 6))
+    for n, j in enumerate(rows):
+        out[:, n, :] = np.random.default_rng([field_seed, j]).random((nz + 6, nx + 6)).T
+    return out
+
+
+def _full_size_worker(rank, world, port, domain, mode, results):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import native
+    from stencil_benchmarks_b200 import distributed
+    from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 2) // world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nx, ny_global, nz = domain
+        start, ny = distributed.split_rows(ny_global, world)[rank]
+        bench = horizontal_diffusion.Fused(domain=(nx, ny, nz), halo=(3, 3, 3), verify=False, device=rank)
+        data = bench.data()
+        rows = range(start, start + ny + 6)
+        true_inp = _global_rows(1, rows, nx, nz)
+        data.inp[...] = true_inp
+        data.coeff[...] = _global_rows(2, rows, nx, nz)
+        lower, upper = distributed.neighbours(rank, world)
+        if lower is not None:
+            data.inp[:, :3, :] = -7.0  # the sweep has to fetch these rows from the neighbour
+        if upper is not None:
+            data.inp[:, 3 + ny:, :] = -7.0
+        mirrors = bench._device_fields(data)
+        bench.upload(data, mirrors)
+        ptr = {n: bench.interior_ptr(mirrors[n][1], h).value for n, h in zip(bench.args, data)}
+        _, _, _, _, sy, sz = bench.geometry()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        if mode == "nccl":
+            exchange = distributed.cuda_halo_exchange(rank, world, "float64", nx, ny, nz, 3, sy, sz, width=3)
+            exchange.finish(ptr["inp"], exchange.start(ptr["inp"]))
+            capi.library().sb200_hdiff(capi.F64, ptr["inp"], ptr["coeff"], ptr["out"], nx, ny, nz, 1, sy, sz,
+                                       0, None, stream)
+            peers = None
+        else:
+            peers = distributed.PeerSlabs(dist, rank, world, mirrors["inp"][0].ptr, ptr["inp"], ny, sz)
+            capi.library().sb200_hdiff_peer(capi.F64, ptr["inp"], ptr["coeff"], ptr["out"], peers.lower,
+                                            peers.ny_lower, peers.sz_lower, peers.upper, peers.ny_upper,
+                                            peers.sz_upper, nx, ny, nz, 1, sy, sz, 0, None, stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if peers is not None:
+            peers.close()
+        bench.download(data, mirrors)
+        # the oracle sees the rows of the GLOBAL field; stencils are local, so the slab with its
+        # true halo rows is all it needs
+        data.inp[...] = true_inp
+        expected = bench.empty_field()  # same padded strides as the other fields
+        expected[...] = 0.0
+        native.hdiff(data.inp, data.coeff, expected, (3, 3, 3))
+        inner = bench.inner_slice()
+        results[rank] = bool(np.allclose(data.out[inner], expected[inner], rtol=1e-13, atol=1e-14))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_strong_scaled_full_size_hdiff(mode):
+    """BASELINE's 2048x2048x80 float64 domain split over every GPU of the box."""
+    import torch.multiprocessing as mp
+
+    world = min(capi.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs two GPUs")
+    results = mp.Manager().dict()
+    mp.spawn(_full_size_worker, args=(world, _free_port(), (2048, 2048, 80), mode, results),
+             nprocs=world, join=True)
+    assert dict(results) == {rank: True for rank in range(world)}
