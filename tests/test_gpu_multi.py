@@ -180,3 +180,64 @@ def test_strong_scaled_full_size_hdiff(mode):
     mp.spawn(_full_size_worker, args=(world, _free_port(), (2048, 2048, 80), mode, results),
              nprocs=world, join=True)
     assert dict(results) == {rank: True for rank in range(world)}
+
+
+def _basic_worker(rank, world, port, case, results):
+    """J-partitioned basic stencils with a j reach (same machinery as hdiff, width 1)."""
+    import torch
+    import torch.distributed as dist
+
+    from stencil_benchmarks_b200 import distributed
+    from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import basic
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nx, ny_global, nz = domain = (260, 67, 6)
+        halo = (1, 1, 1)
+        shape = tuple(d + 2 * h for d, h in zip(domain, halo))
+        g_inp = np.random.default_rng(5).random(shape)
+        start, ny = distributed.split_rows(ny_global, world)[rank]
+        if case == "laplacian":
+            bench = basic.Laplacian(domain=(nx, ny, nz), halo=halo, verify=False, device=rank)
+            expected = stencils.laplacian(g_inp, halo, along=(True, True, False))
+        elif case == "symmetric":
+            bench = basic.SymmetricAverage(domain=(nx, ny, nz), halo=halo, axis=1, verify=False, device=rank)
+            expected = stencils.symmetric_average(g_inp, halo, axis=1)
+        else:
+            bench = basic.OnesidedAverage(domain=(nx, ny, nz), halo=halo, axis=1, verify=False, device=rank)
+            expected = stencils.onesided_average(g_inp, halo, axis=1)
+        data = bench.data()
+        data.inp[...] = g_inp[:, start:start + ny + 2, :]
+        lower, upper = distributed.neighbours(rank, world)
+        if lower is not None:
+            data.inp[:, :1, :] = -7.0  # to be replaced by the neighbour's last interior row
+        if upper is not None:
+            data.inp[:, 1 + ny:, :] = -7.0
+        mirrors = bench._device_fields(data)
+        bench.upload(data, mirrors)
+        pointers = {n: bench.interior_ptr(mirrors[n][1], h) for n, h in zip(bench.args, data)}
+        _, _, _, _, sy, sz = bench.geometry()
+        exchange = distributed.cuda_halo_exchange(rank, world, "float64", nx, ny, nz, halo[0], sy, sz, width=1)
+        exchange.finish(pointers["inp"].value, exchange.start(pointers["inp"].value))
+        bench.launch(pointers, 0, None, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        bench.download(data, mirrors)
+        ok = np.allclose(data.out[1:-1, 1:1 + ny, 1:-1], expected[1:-1, 1 + start:1 + start + ny, 1:-1],
+                         rtol=1e-13, atol=1e-14)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["laplacian", "symmetric", "onesided"])
+def test_partitioned_basic_matches_global_oracle(case):
+    import torch.multiprocessing as mp
+
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    results = mp.Manager().dict()
+    mp.spawn(_basic_worker, args=(2, _free_port(), case, results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}
