@@ -150,4 +150,15 @@ inline bool aligned_to(const void* p, size_t bytes) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// SMs of the current device (every GPU of a box is the same part: cached once per process)
+inline int sm_count() {
+  static int count = [] {
+    int device = 0, n = 148;
+    if (cudaGetDevice(&device) == cudaSuccess)
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n;
+  }();
+  return count;
+}
+
 }  // namespace sb200

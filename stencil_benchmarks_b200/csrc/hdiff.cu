@@ -221,13 +221,28 @@ struct PeerMaps {
   int has_lower, has_upper;
 };
 
+// Work decomposition of one sweep: CTA = (256-wide i tile, segment of jt rows, level k), numbered
+// i-tile fastest, then segment, then level.  CTAs start in that order, so the last levels form the
+// tail of the launch, when SMs run dry one by one: the levels are split into regimes with shorter
+// and shorter segments, which makes the tail as long as a short CTA instead of a long one at the
+// price of re-reading 4 rows per short segment on the last levels.
+struct HdiffTiling {
+  static constexpr int kMax = 4;
+  int xtiles;
+  int regimes;            // 1 ... kMax, regime 0 first
+  int first_cta[kMax];    // linear index of a regime's first CTA
+  int first_k[kMax];      // its first level
+  int segments[kMax];     // segments per (i tile, level)
+  int jt[kMax];           // rows per segment
+};
+
 template <class T, int R, int S, bool PEER>
 __global__ void __launch_bounds__(tmacfg::kThreads, 4)
     hdiff_tma_kernel(const __grid_constant__ CUtensorMap map_inp,
                      const __grid_constant__ CUtensorMap map_halo,
                      const __grid_constant__ CUtensorMap map_coeff,
                      const __grid_constant__ PeerMaps peer, T* __restrict__ out, int nx,
-                     int ny, int jt, int64_t sy, int64_t sz, int hint_mode) {
+                     int ny, const HdiffTiling tiling, int64_t sy, int64_t sz, int hint_mode) {
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
   constexpr int STAGE = tmacfg::stage_bytes(R);
@@ -235,10 +250,19 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE);
   uint64_t* empty = full + S;
 
-  const int it = blockIdx.x * TW;  // first i of the tile
-  const int jb = blockIdx.y * jt;
+  int b = int(blockIdx.x), regime = 0;
+#pragma unroll
+  for (int q = 1; q < HdiffTiling::kMax; ++q)
+    if (q < tiling.regimes && b >= tiling.first_cta[q]) regime = q;
+  b -= tiling.first_cta[regime];
+  const int segments = tiling.segments[regime], jt = tiling.jt[regime];
+  int k = tiling.first_k[regime];
+  const int xt = b % tiling.xtiles;
+  b /= tiling.xtiles;
+  k += b / segments;
+  const int it = xt * TW;  // first i of the tile
+  const int jb = (b % segments) * jt;
   const int je = min(jb + jt, ny);
-  const int k = blockIdx.z;
   const int nstages = (je - jb + 4 + R - 1) / R;  // rows jb-2 .. je+1
   const int warp = threadIdx.x >> 5;
 
@@ -396,18 +420,21 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
   }
 }
 
-// SB200_HDIFF_CFG="variant,jt": variant 0 = auto, 1 = jmarch, 2 = tma; jt = rows per CTA (0 = auto)
+// SB200_HDIFF_CFG="variant,jt,hint_mode,pipeline,tail": variant 0 = auto, 1 = jmarch, 2 = tma;
+// jt = rows per CTA (0 = auto); tail = levels swept with short segments at the end of the launch
+// (0 = auto, -1 = none)
 struct HdiffConfig {
   int variant = 0;
   int jt = 0;
   int hint_mode = 0;
   int pipeline = 0;
+  int tail = 0;
 };
 
 inline HdiffConfig hdiff_config() {
   HdiffConfig cfg;
   if (const char* env = std::getenv("SB200_HDIFF_CFG"))
-    std::sscanf(env, "%d,%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode, &cfg.pipeline);
+    std::sscanf(env, "%d,%d,%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode, &cfg.pipeline, &cfg.tail);
   return cfg;
 }
 
@@ -468,15 +495,74 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
   const int64_t xtiles = ceil_div(nx, TW);
   int jt = jt_request;
   if (jt <= 0) {
-    // enough CTAs for ~8 per SM, but long marches where the domain allows it
+    // enough CTAs for ~8 per SM; otherwise 32-row segments.  Longer marches re-read fewer rows
+    // (4 per segment, and those mostly hit L2 because neighbouring segments run concurrently) but
+    // measure slower: 128 rows 1.242 ms, 48: 1.229, 32: 1.196, 24: 1.175, 16: 1.167, 8: 1.519 for
+    // a single sweep; in a long loop under the board's power cap 32 rows is the fastest
+    // (1.222-1.228 vs 1.248 ms with 128, 1.250 with 24) -- profiles/hdiff_segments_r01.log
     const int64_t target = 148 * 8;
     int64_t segments = ceil_div(target, xtiles * nz);
-    jt = int(std::min<int64_t>(128, std::max<int64_t>(16, ceil_div(ny, segments))));
+    jt = int(std::min<int64_t>(32, std::max<int64_t>(16, ceil_div(ny, segments))));
   }
   jt = int(ceil_div(jt, R)) * R;
-  const dim3 grid(unsigned(xtiles), unsigned(ceil_div(ny, jt)), unsigned(nz));
-  if (grid.y > 65535u || grid.z > 65535u) return fail("sb200_hdiff: domain too large for the launch grid");
   constexpr int smem = tmacfg::smem_bytes(R, S);
+  int64_t ctas_total = 0;
+  HdiffTiling tiling;
+  tiling.xtiles = int(xtiles);
+  {
+    // regimes after the first: (rows per segment, levels), from SB200_HDIFF_TAIL="jt:levels,..."
+    // or the default grading
+    int tail_jt[HdiffTiling::kMax - 1], tail_nz[HdiffTiling::kMax - 1], tails = 0;
+    const int mode = hdiff_config().tail;
+    if (const char* spec = std::getenv("SB200_HDIFF_TAIL")) {
+      while (tails < HdiffTiling::kMax - 1 && *spec) {
+        int a = 0, b = 0, used_chars = 0;
+        if (std::sscanf(spec, "%d:%d%n", &a, &b, &used_chars) != 2 || a <= 0 || b < 0) break;
+        tail_jt[tails] = int(ceil_div(a, R)) * R;
+        tail_nz[tails] = b;
+        ++tails;
+        spec += used_chars;
+        if (*spec == ',') ++spec;
+      }
+    } else if (mode >= 0 && jt >= 64) {
+      // about 1.5 waves of long CTAs' worth of work with quarter-length segments, at most half
+      // of the levels
+      const int64_t resident = int64_t(sm_count()) * std::min<int64_t>(4, (227 * 1024) / smem);
+      const int64_t per_level = xtiles * ceil_div(ny, jt);
+      tail_jt[0] = int(ceil_div(jt / 4, R)) * R;
+      tail_nz[0] = mode > 0 ? mode : int(std::min<int64_t>(nz / 2, ceil_div(3 * resident / 2, per_level)));
+      tails = 1;
+    }
+    int levels_left = int(nz);
+    for (int q = 0; q < tails; ++q) {
+      tail_nz[q] = std::min(tail_nz[q], levels_left);
+      levels_left -= tail_nz[q];
+    }
+    tiling.regimes = 0;
+    int64_t cta = 0;
+    int level = 0;
+    for (int q = 0; q <= tails; ++q) {
+      const int rows = q == 0 ? jt : tail_jt[q - 1];
+      const int levels = q == 0 ? levels_left : tail_nz[q - 1];
+      if (levels == 0) continue;
+      const int r = tiling.regimes++;
+      tiling.first_cta[r] = int(cta);
+      tiling.first_k[r] = level;
+      tiling.jt[r] = rows;
+      tiling.segments[r] = int(ceil_div(ny, rows));
+      cta += xtiles * tiling.segments[r] * levels;
+      level += levels;
+      if (cta > 0x7fffffff) return fail("sb200_hdiff: domain too large for the launch grid");
+    }
+    for (int r = tiling.regimes; r < HdiffTiling::kMax; ++r) {
+      tiling.first_cta[r] = 0x7fffffff;
+      tiling.first_k[r] = 0;
+      tiling.segments[r] = 1;
+      tiling.jt[r] = R;
+    }
+    ctas_total = cta;
+  }
+  const dim3 grid{unsigned(ctas_total), 1, 1};
   // per launch: the attribute is per device, and a process may drive several devices
   SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -486,10 +572,10 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
   auto launch = [&] {
     if (with_peers)
       hdiff_tma_kernel<T, R, S, true><<<grid, tmacfg::kThreads, smem, stream>>>(
-          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), jt, sy, sz, hint_mode);
+          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
     else
       hdiff_tma_kernel<T, R, S, false><<<grid, tmacfg::kThreads, smem, stream>>>(
-          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), jt, sy, sz, hint_mode);
+          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);

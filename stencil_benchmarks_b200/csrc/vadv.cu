@@ -652,16 +652,6 @@ inline int vadv_variant_override() {
   return 0;
 }
 
-inline int sm_count() {
-  static int count = [] {
-    int device = 0, n = 148;
-    if (cudaGetDevice(&device) == cudaSuccess)
-      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
-    return n;
-  }();
-  return count;
-}
-
 template <class T>
 int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage, const T* wcon,
                        int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz, int ishift,
