@@ -214,3 +214,13 @@ def test_bench_accounting_and_config():
     assert "NCCL" in bench.workload_config("hdiff", 2, "nccl")["halo_exchange"]
     peak, source = bench.measured_peak()
     assert peak > 1000 and ("measured" in source or "fallback" in source)
+    # strong scaling: the BASELINE domain is split into J slabs, the job's bytes are the slabs' bytes
+    assert bench.local_domain("hdiff", 8, 3, "strong") == (2048, 256, 80)
+    assert bench.local_domain("hdiff", 3, 0, "strong") == (2048, 683, 80)
+    assert bench.local_domain("hdiff", 3, 2, "strong") == (2048, 682, 80)
+    assert bench.local_domain("hdiff", 8, 3, "weak") == (2048, 2048, 80)
+    assert bench.local_domain("hdiff", 1, 0, "strong") == (2048, 2048, 80)
+    strong = bench.workload_config("hdiff", 8, "peer", "strong")
+    assert strong["global_domain"] == [2048, 2048, 80] and strong["per_gpu_domain"] == [2048, 256, 80]
+    assert strong["bytes_per_step_per_gpu"] == bench.algorithmic_bytes("hdiff", (2048, 256, 80))
+    assert sum(bench.local_domain("vadv", 4, r, "strong")[1] for r in range(4)) == 1024
