@@ -180,6 +180,16 @@ int sb200_hdiff(int dtype, const void* inp, const void* coeff, void* out,
                 int64_t sx, int64_t sy, int64_t sz,
                 int dry_runs, double* time, void* stream);
 
+/* Work decomposition sb200_hdiff uses for a domain on its TMA path (host only, no
+ * device needed; no counterpart in the reference, whose block sizes are template
+ * literals: cuda_hip/horizontal_diffusion.py:41).  CTA b of `*ctas` belongs to the
+ * last regime r with b >= first_cta[r]; with c = b - first_cta[r] it sweeps i tile
+ * c % *xtiles, rows [s*jt, min((s+1)*jt, ny)) with s = (c / *xtiles) % segments, on
+ * level first_k[r] + c / (*xtiles * segments).  `table` receives 4 regimes x
+ * {first_cta, first_k, segments, jt}; `*regimes` of them are in use. */
+int sb200_hdiff_tiling(int dtype, int64_t nx, int64_t ny, int64_t nz,
+                       int* xtiles, int* regimes, int* table, int64_t* ctas);
+
 /* Vertical advection, u component (oracle: sb/bc/stencils/base.py:349-501 with
  * all_components=False; reference GPU variants:
  * sb/bc/stencils/cuda_hip/vertical_advection.py:60-73).  Per-(i,j)-column Thomas

@@ -71,6 +71,8 @@ PROTOTYPES = {
     "sb200_stream_op": (_i, [_i, _i, _vp, _vp, _vp, _u64, ctypes.c_double, _i, _dp, _vp]),
     "sb200_basic": (_i, [_i, _i, _vp, _vp] + _geom + [_i, _i, _i, _dp, _vp]),
     "sb200_hdiff": (_i, [_i, _vp, _vp, _vp] + _geom + [_i, _dp, _vp]),
+    "sb200_hdiff_tiling": (_i, [_i, _i64, _i64, _i64, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
+                                ctypes.POINTER(_i64)]),
     "sb200_hdiff_peer": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64] + _geom + [_i, _dp, _vp]),
     "sb200_ipc_get_handle": (_i, [_vp, _vp]),
     "sb200_ipc_open_handle": (_i, [_vp, ctypes.POINTER(_vp)]),

@@ -438,6 +438,77 @@ inline HdiffConfig hdiff_config() {
   return cfg;
 }
 
+// Segments and regimes of one sweep (host only, no CUDA call unless a graded tail is requested).
+// R = rows per TMA stage, smem = dynamic shared memory per CTA.
+inline bool hdiff_make_tiling(int R, int smem, int64_t xtiles, int64_t ny, int64_t nz, int jt_request,
+                              HdiffTiling& tiling, int64_t& ctas_total) {
+  int jt = jt_request;
+  if (jt <= 0) {
+    // enough CTAs for ~8 per SM; otherwise 32-row segments.  Longer marches re-read fewer rows
+    // (4 per segment, and those mostly hit L2 because neighbouring segments run concurrently) but
+    // measure slower: 128 rows 1.242 ms, 48: 1.229, 32: 1.196, 24: 1.175, 16: 1.167, 8: 1.519 for
+    // a single sweep; in a long loop under the board's power cap 32 rows is the fastest
+    // (1.222-1.228 vs 1.248 ms with 128, 1.250 with 24) -- profiles/hdiff_segments_r01.log
+    const int64_t target = 148 * 8;
+    int64_t segments = ceil_div(target, xtiles * nz);
+    jt = int(std::min<int64_t>(32, std::max<int64_t>(16, ceil_div(ny, segments))));
+  }
+  jt = int(ceil_div(jt, R)) * R;
+  tiling.xtiles = int(xtiles);
+  // regimes after the first: (rows per segment, levels), from SB200_HDIFF_TAIL="jt:levels,..."
+  // or, for requested segments of 64 rows and more, a default grading
+  int tail_jt[HdiffTiling::kMax - 1], tail_nz[HdiffTiling::kMax - 1], tails = 0;
+  const int mode = hdiff_config().tail;
+  if (const char* spec = std::getenv("SB200_HDIFF_TAIL")) {
+    while (tails < HdiffTiling::kMax - 1 && *spec) {
+      int a = 0, b = 0, used_chars = 0;
+      if (std::sscanf(spec, "%d:%d%n", &a, &b, &used_chars) != 2 || a <= 0 || b < 0) break;
+      tail_jt[tails] = int(ceil_div(a, R)) * R;
+      tail_nz[tails] = b;
+      ++tails;
+      spec += used_chars;
+      if (*spec == ',') ++spec;
+    }
+  } else if (mode >= 0 && jt >= 64) {
+    // about 1.5 waves of long CTAs' worth of work with quarter-length segments, at most half
+    // of the levels
+    const int64_t resident = int64_t(sm_count()) * std::min<int64_t>(4, (227 * 1024) / smem);
+    const int64_t per_level = xtiles * ceil_div(ny, jt);
+    tail_jt[0] = int(ceil_div(jt / 4, R)) * R;
+    tail_nz[0] = mode > 0 ? mode : int(std::min<int64_t>(nz / 2, ceil_div(3 * resident / 2, per_level)));
+    tails = 1;
+  }
+  int levels_left = int(nz);
+  for (int q = 0; q < tails; ++q) {
+    tail_nz[q] = std::min(tail_nz[q], levels_left);
+    levels_left -= tail_nz[q];
+  }
+  tiling.regimes = 0;
+  int64_t cta = 0;
+  int level = 0;
+  for (int q = 0; q <= tails; ++q) {
+    const int rows = q == 0 ? jt : tail_jt[q - 1];
+    const int levels = q == 0 ? levels_left : tail_nz[q - 1];
+    if (levels == 0) continue;
+    const int r = tiling.regimes++;
+    tiling.first_cta[r] = int(cta);
+    tiling.first_k[r] = level;
+    tiling.jt[r] = rows;
+    tiling.segments[r] = int(ceil_div(ny, rows));
+    cta += xtiles * tiling.segments[r] * levels;
+    level += levels;
+    if (cta > 0x7fffffff) return false;
+  }
+  for (int r = tiling.regimes; r < HdiffTiling::kMax; ++r) {
+    tiling.first_cta[r] = 0x7fffffff;
+    tiling.first_k[r] = 0;
+    tiling.segments[r] = 1;
+    tiling.jt[r] = R;
+  }
+  ctas_total = cta;
+  return true;
+}
+
 template <class T, int R, int S>
 int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
                      int64_t sy, int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
@@ -493,75 +564,11 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
   }
 
   const int64_t xtiles = ceil_div(nx, TW);
-  int jt = jt_request;
-  if (jt <= 0) {
-    // enough CTAs for ~8 per SM; otherwise 32-row segments.  Longer marches re-read fewer rows
-    // (4 per segment, and those mostly hit L2 because neighbouring segments run concurrently) but
-    // measure slower: 128 rows 1.242 ms, 48: 1.229, 32: 1.196, 24: 1.175, 16: 1.167, 8: 1.519 for
-    // a single sweep; in a long loop under the board's power cap 32 rows is the fastest
-    // (1.222-1.228 vs 1.248 ms with 128, 1.250 with 24) -- profiles/hdiff_segments_r01.log
-    const int64_t target = 148 * 8;
-    int64_t segments = ceil_div(target, xtiles * nz);
-    jt = int(std::min<int64_t>(32, std::max<int64_t>(16, ceil_div(ny, segments))));
-  }
-  jt = int(ceil_div(jt, R)) * R;
   constexpr int smem = tmacfg::smem_bytes(R, S);
-  int64_t ctas_total = 0;
   HdiffTiling tiling;
-  tiling.xtiles = int(xtiles);
-  {
-    // regimes after the first: (rows per segment, levels), from SB200_HDIFF_TAIL="jt:levels,..."
-    // or the default grading
-    int tail_jt[HdiffTiling::kMax - 1], tail_nz[HdiffTiling::kMax - 1], tails = 0;
-    const int mode = hdiff_config().tail;
-    if (const char* spec = std::getenv("SB200_HDIFF_TAIL")) {
-      while (tails < HdiffTiling::kMax - 1 && *spec) {
-        int a = 0, b = 0, used_chars = 0;
-        if (std::sscanf(spec, "%d:%d%n", &a, &b, &used_chars) != 2 || a <= 0 || b < 0) break;
-        tail_jt[tails] = int(ceil_div(a, R)) * R;
-        tail_nz[tails] = b;
-        ++tails;
-        spec += used_chars;
-        if (*spec == ',') ++spec;
-      }
-    } else if (mode >= 0 && jt >= 64) {
-      // about 1.5 waves of long CTAs' worth of work with quarter-length segments, at most half
-      // of the levels
-      const int64_t resident = int64_t(sm_count()) * std::min<int64_t>(4, (227 * 1024) / smem);
-      const int64_t per_level = xtiles * ceil_div(ny, jt);
-      tail_jt[0] = int(ceil_div(jt / 4, R)) * R;
-      tail_nz[0] = mode > 0 ? mode : int(std::min<int64_t>(nz / 2, ceil_div(3 * resident / 2, per_level)));
-      tails = 1;
-    }
-    int levels_left = int(nz);
-    for (int q = 0; q < tails; ++q) {
-      tail_nz[q] = std::min(tail_nz[q], levels_left);
-      levels_left -= tail_nz[q];
-    }
-    tiling.regimes = 0;
-    int64_t cta = 0;
-    int level = 0;
-    for (int q = 0; q <= tails; ++q) {
-      const int rows = q == 0 ? jt : tail_jt[q - 1];
-      const int levels = q == 0 ? levels_left : tail_nz[q - 1];
-      if (levels == 0) continue;
-      const int r = tiling.regimes++;
-      tiling.first_cta[r] = int(cta);
-      tiling.first_k[r] = level;
-      tiling.jt[r] = rows;
-      tiling.segments[r] = int(ceil_div(ny, rows));
-      cta += xtiles * tiling.segments[r] * levels;
-      level += levels;
-      if (cta > 0x7fffffff) return fail("sb200_hdiff: domain too large for the launch grid");
-    }
-    for (int r = tiling.regimes; r < HdiffTiling::kMax; ++r) {
-      tiling.first_cta[r] = 0x7fffffff;
-      tiling.first_k[r] = 0;
-      tiling.segments[r] = 1;
-      tiling.jt[r] = R;
-    }
-    ctas_total = cta;
-  }
+  int64_t ctas_total = 0;
+  if (!hdiff_make_tiling(R, smem, xtiles, ny, nz, jt_request, tiling, ctas_total))
+    return fail("sb200_hdiff: domain too large for the launch grid");
   const dim3 grid{unsigned(ctas_total), 1, 1};
   // per launch: the attribute is per device, and a process may drive several devices
   SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S, false>,
@@ -684,6 +691,32 @@ extern "C" int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, v
   }
   if (rc == 0 && !used) return fail("sb200_hdiff_peer: the TMA path is not available for these fields");
   return rc;
+}
+
+extern "C" int sb200_hdiff_tiling(int dtype, int64_t nx, int64_t ny, int64_t nz, int* xtiles, int* regimes,
+                                  int* table, int64_t* ctas) {
+  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sb200_hdiff_tiling: domain must be positive");
+  if (dtype != SB200_F64 && dtype != SB200_F32) return fail("sb200_hdiff_tiling: unsupported dtype");
+  if (xtiles == nullptr || regimes == nullptr || table == nullptr || ctas == nullptr)
+    return fail("sb200_hdiff_tiling: null output pointer");
+  // the default ring: 4 rows per stage, 4 stages (launch_hdiff_tma)
+  constexpr int R = 4, S = 4;
+  const int tile_width = tmacfg::kConsumers * (dtype == SB200_F64 ? VecN<double>::value : VecN<float>::value);
+  HdiffTiling tiling;
+  int64_t total = 0;
+  if (!hdiff_make_tiling(R, tmacfg::smem_bytes(R, S), ceil_div(nx, tile_width), ny, nz, hdiff_config().jt, tiling,
+                         total))
+    return fail("sb200_hdiff_tiling: domain too large for the launch grid");
+  *xtiles = tiling.xtiles;
+  *regimes = tiling.regimes;
+  for (int r = 0; r < HdiffTiling::kMax; ++r) {
+    table[4 * r + 0] = tiling.first_cta[r];
+    table[4 * r + 1] = tiling.first_k[r];
+    table[4 * r + 2] = tiling.segments[r];
+    table[4 * r + 3] = tiling.jt[r];
+  }
+  *ctas = total;
+  return 0;
 }
 
 extern "C" int sb200_hdiff(int dtype, const void* inp, const void* coeff, void* out, int64_t nx,

@@ -224,3 +224,46 @@ def test_bench_accounting_and_config():
     assert strong["global_domain"] == [2048, 2048, 80] and strong["per_gpu_domain"] == [2048, 256, 80]
     assert strong["bytes_per_step_per_gpu"] == bench.algorithmic_bytes("hdiff", (2048, 256, 80))
     assert sum(bench.local_domain("vadv", 4, r, "strong")[1] for r in range(4)) == 1024
+
+
+def _hdiff_tiles(dtype, domain):
+    """Every CTA's (i tile, level, first row, last row) decoded the way hdiff_tma_kernel does."""
+    import ctypes
+
+    lib = capi.library()
+    xtiles, regimes, ctas = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+    table = (ctypes.c_int * 16)()
+    lib.sb200_hdiff_tiling(capi.dtype_code(dtype), *domain, ctypes.byref(xtiles), ctypes.byref(regimes),
+                           table, ctypes.byref(ctas))
+    first_cta, first_k, segments, jt = (np.array(table[i::4][:regimes.value]) for i in range(4))
+    b = np.arange(ctas.value)
+    regime = np.searchsorted(first_cta, b, side="right") - 1
+    c = b - first_cta[regime]
+    xt = c % xtiles.value
+    seg = (c // xtiles.value) % segments[regime]
+    k = first_k[regime] + c // (xtiles.value * segments[regime])
+    j0 = seg * jt[regime]
+    j1 = np.minimum(j0 + jt[regime], domain[1])
+    return xtiles.value, xt, k, j0, j1
+
+
+@pytest.mark.parametrize("tail", [None, "64:3,32:2,16:1", "16:100", "8:1"])
+@pytest.mark.parametrize("dtype,domain", [("float64", (2048, 2048, 80)), ("float64", (300, 67, 5)),
+                                          ("float32", (1000, 33, 7)), ("float64", (64, 1, 1)),
+                                          ("float32", (513, 4100, 2))])
+def test_hdiff_tiling_covers_every_row_once(monkeypatch, dtype, domain, tail):
+    """The work decomposition of the TMA kernel (uniform segments or graded regimes) is a partition:
+    every (i tile, level, row) belongs to exactly one CTA (include/sbench_b200.h: sb200_hdiff_tiling)."""
+    if tail is not None:
+        monkeypatch.setenv("SB200_HDIFF_TAIL", tail)
+    nx, ny, nz = domain
+    xtiles, xt, k, j0, j1 = _hdiff_tiles(dtype, domain)
+    tile_width = 128 * (2 if dtype == "float64" else 4)
+    assert xtiles == -(-nx // tile_width)
+    assert (j1 > j0).all() and k.min() == 0 and k.max() == nz - 1 and xt.max() == xtiles - 1
+    rows = np.zeros((xtiles, nz, ny), dtype=np.int32)
+    for a, b_, c, d in zip(xt, k, j0, j1):
+        rows[a, b_, c:d] += 1
+    assert (rows == 1).all()
+    if tail is None:
+        assert (j1 - j0).max() <= 32  # default segments (profiles/hdiff_segments_r01.log)
