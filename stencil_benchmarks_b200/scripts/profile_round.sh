@@ -39,4 +39,16 @@ timeout 600 python -m oracle.ref_cuda --repeat 11 --out $out/reference_cuda_${ta
 
 # 6. all kernels, both dtypes, for the table in profiles/README.md
 timeout 600 $KB --repeat 20 --out $out/kernels_${tag}.json > $out/kernels_${tag}.log 2>&1
+
+# 7. hdiff: rows per march segment, single sweeps and the long loop of bench.py (the two disagree
+#    under the board's power cap: profiles/hdiff_segments_r01.log)
+{
+  for jt in 16 24 32 64 128; do
+    echo "== SB200_HDIFF_CFG=0,$jt (single sweeps)"
+    SB200_HDIFF_CFG=0,$jt timeout 120 $KB --what hdiff --dtypes float64 --repeat 30 2>&1 | grep hdiff
+    echo "== SB200_HDIFF_CFG=0,$jt (bench.py loop)"
+    SB200_HDIFF_CFG=0,$jt timeout 300 python bench.py --steps 300 --warmup 10 --no-extras --no-cpu-baseline \
+        --e2e-steps 1 | python -c "import sys, json; d = json.loads(sys.stdin.readline()); print(d['ms_per_step'], d['clocks'])"
+  done
+} > $out/hdiff_segments_${tag}.log 2>&1
 ls -la $out
