@@ -6,8 +6,11 @@
     python bench.py --impl reference ...      # the reference's own OpenMP CPU kernels
 
 Workload (BASELINE.json): horizontal diffusion 2048x2048x80 float64 per GPU (weak scaling:
-the global domain is 2048 x 2048*N x 80, J-partitioned, width-3 halos exchanged with NCCL
-send/recv every sweep, overlapped with the interior kernel).  One "step" = one sweep.
+the global domain is 2048 x 2048*N x 80, J-partitioned; `--scaling strong` splits the single
+2048x2048x80 domain instead).  The width-2 halo rows a sweep needs from its neighbours are read
+by the sweep itself from the neighbour GPU's memory (CUDA IPC over NVLink, `--exchange peer`,
+default) or exchanged as width-3 halos with NCCL send/recv overlapped with the interior rows
+(`--exchange nccl`).  One "step" = one sweep.
 `value` counts the ALGORITHMIC bytes of SURVEY.md §8d, (2*N + (nx+4)(ny+4)nz)*8 per GPU,
 not the larger sbench figure.  Fields (8.7 GB per GPU) are far larger than the 126 MB L2,
 so no L2 flush is needed between steps.
