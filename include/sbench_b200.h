@@ -207,6 +207,23 @@ int sb200_vadv(int dtype, const void* ustage, const void* upos, const void* uten
                int ishift, int jshift, int variant,
                int dry_runs, double* time, void* stream);
 
+/* Vertical advection of `ncomp` = 1...3 components in ONE sweep (all_components=True, oracle
+ * base.py:475-483; reference counterpart: the merged u/v/w kernel
+ * sb/bc/stencils/cuda_hip/templates/vertical_advection_localmemmerged.j2:392-462).  Component c
+ * solves its own system from ustage[c] / upos[c] / utens[c] / utensstage[c] with the wcon
+ * neighbour (ishift[c], jshift[c]); all components share `wcon`, which the on-chip variant reads
+ * from HBM once per sweep (the components of a column batch are swept by different SMs at the same
+ * time and meet in the L2): 13 reads + 3 writes per point for u, v, w instead of 3 x (5 + 1).
+ * The tables hold `ncomp` entries; everything else as for sb200_vadv. */
+int sb200_vadv_components(int dtype, int ncomp,
+                          const void* const* ustage, const void* const* upos,
+                          const void* const* utens, void* const* utensstage,
+                          const int* ishift, const int* jshift,
+                          const void* wcon, void* ccol, void* dcol,
+                          int64_t nx, int64_t ny, int64_t nz,
+                          int64_t sx, int64_t sy, int64_t sz,
+                          int variant, int dry_runs, double* time, void* stream);
+
 /* ------------------------------------------------------------------ */
 /* Multi-GPU halo plumbing for the J-partitioned horizontal diffusion  */
 /* ------------------------------------------------------------------ */

@@ -52,6 +52,19 @@ def prepare_reference():
     sys.path.insert(0, str(SCRATCH))
 
 
+def install_package():
+    """The reference's Python package, with its two pybind11 helpers built, as oracle/_ref/pkg:
+    TEST infrastructure that travels to the GPU box (which has no /root/reference), so that the
+    `-m gpu` drop-in tests can run the B200 classes under the reference's own ``Stencil.run()`` /
+    ``verify_stencil`` / CLI.  Build output only -- oracle/_ref/ is git-ignored."""
+    target = OUT / "pkg" / "stencil_benchmarks"
+    if target.exists():
+        shutil.rmtree(target)
+    shutil.copytree(SCRATCH / "stencil_benchmarks", target,
+                    ignore=shutil.ignore_patterns("__pycache__", "*.cpp", "test"))
+    return target
+
+
 def configurations():
     from stencil_benchmarks.benchmarks_collection.stencils.openmp import (
         basic,
@@ -155,6 +168,8 @@ def main():
         print("no /root/reference here: keeping the prebuilt oracle/_ref as it is")
         return 0
     prepare_reference()
+    OUT.mkdir(parents=True, exist_ok=True)
+    install_package()
     from stencil_benchmarks.benchmarks_collection.stencils import base
     from stencil_benchmarks.tools import compilation
 

@@ -2,8 +2,8 @@
 
 Counterpart of the four reference variants in
 stencil_benchmarks/benchmarks_collection/stencils/cuda_hip/vertical_advection.py:60-73.
-With ``all_components`` the u, v and w solves run one after the other with the
-wcon neighbour of each (base.py:475-483).
+With ``all_components`` the u, v and w systems are solved in one sweep that shares
+the wcon field (base.py:475-483; the reference's ``LocalMemMerged``).
 """
 
 import ctypes
@@ -47,18 +47,19 @@ class VerticalAdvectionMixin(StencilMixin):
         components = [("u", 1, 0)]
         if self.all_components:
             components += [("v", 0, 1), ("w", 0, 0)]
-        total = 0.0
-        for index, (c, ishift, jshift) in enumerate(components):
-            elapsed = ctypes.c_double()
-            self._lib.sb200_vadv(
-                self._dtype_code, pointers[c + "stage"], pointers[c + "pos"], pointers[c + "tens"],
-                pointers[c + "tensstage"], pointers["wcon"], pointers["ccol"], pointers["dcol"],
-                pointers["datacol"], *self.geometry(domain), ishift, jshift, variant,
-                dry_runs, ctypes.byref(elapsed) if time_ptr is not None else None, _vp(stream),
-            )
-            total += elapsed.value
-        if time_ptr is not None:
-            ctypes.cast(time_ptr, ctypes.POINTER(ctypes.c_double))[0] = total
+        n = len(components)
+
+        def table(suffix):
+            return (_vp * n)(*[pointers[c + suffix] for c, _, _ in components])
+
+        # one sweep for all components: they share wcon, which is read from HBM once
+        self._lib.sb200_vadv_components(
+            self._dtype_code, n, table("stage"), table("pos"), table("tens"), table("tensstage"),
+            (ctypes.c_int * n)(*[i for _, i, _ in components]),
+            (ctypes.c_int * n)(*[j for _, _, j in components]),
+            pointers["wcon"], pointers["ccol"], pointers["dcol"], *self.geometry(domain), variant,
+            dry_runs, time_ptr, _vp(stream),
+        )
 
 
 class Thomas(VerticalAdvectionMixin, base.VerticalAdvectionStencil):

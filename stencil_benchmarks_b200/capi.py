@@ -78,6 +78,8 @@ PROTOTYPES = {
     "sb200_ipc_open_handle": (_i, [_vp, ctypes.POINTER(_vp)]),
     "sb200_ipc_close_handle": (_i, [_vp]),
     "sb200_vadv": (_i, [_i] + [_vp] * 8 + _geom + [_i, _i, _i, _i, _dp, _vp]),
+    "sb200_vadv_components": (_i, [_i, _i] + [ctypes.POINTER(_vp)] * 4 + [ctypes.POINTER(_i)] * 2 + [_vp] * 3
+                              + _geom + [_i, _i, _dp, _vp]),
     "sb200_pack_rows": (_i, [_i, _vp, _vp] + [_i64] * 7 + [_vp]),
     "sb200_unpack_rows": (_i, [_i, _vp, _vp] + [_i64] * 7 + [_vp]),
 }

@@ -39,30 +39,39 @@ inline int fail(const char* message) {
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// device counter for a persistent kernel that hands out its work items dynamically (runtime.cu);
+// the caller zeroes it on the launch's stream.  nullptr: no device / out of memory.
+unsigned int* work_counter();
+
 // --- timing wrapper -----------------------------------------------------------
 // dry_runs untimed launches, then one launch bracketed by events on `stream`
 // (base.j2:137-184).  time == nullptr: enqueue only.
+struct EventPair {
+  cudaEvent_t start = nullptr, stop = nullptr;
+  ~EventPair() {
+    if (start != nullptr) cudaEventDestroy(start);
+    if (stop != nullptr) cudaEventDestroy(stop);
+  }
+};
+
 template <class Launch>
 int timed(Launch&& launch, int dry_runs, double* time, cudaStream_t stream) {
+  for (int i = 0; i < dry_runs; ++i) launch();
   if (time == nullptr) {
-    for (int i = 0; i < dry_runs; ++i) launch();
     launch();
     SB200_CHECK(cudaGetLastError());
     return 0;
   }
-  for (int i = 0; i < dry_runs; ++i) launch();
-  cudaEvent_t start, stop;
-  SB200_CHECK(cudaEventCreate(&start));
-  SB200_CHECK(cudaEventCreate(&stop));
-  SB200_CHECK(cudaEventRecord(start, stream));
+  EventPair events;  // destroyed on every path out of here
+  SB200_CHECK(cudaEventCreate(&events.start));
+  SB200_CHECK(cudaEventCreate(&events.stop));
+  SB200_CHECK(cudaEventRecord(events.start, stream));
   launch();
   SB200_CHECK(cudaGetLastError());
-  SB200_CHECK(cudaEventRecord(stop, stream));
-  SB200_CHECK(cudaEventSynchronize(stop));
+  SB200_CHECK(cudaEventRecord(events.stop, stream));
+  SB200_CHECK(cudaEventSynchronize(events.stop));
   float ms = 0.f;
-  SB200_CHECK(cudaEventElapsedTime(&ms, start, stop));
-  SB200_CHECK(cudaEventDestroy(start));
-  SB200_CHECK(cudaEventDestroy(stop));
+  SB200_CHECK(cudaEventElapsedTime(&ms, events.start, events.stop));
   *time = double(ms) / 1000.0;
   return 0;
 }

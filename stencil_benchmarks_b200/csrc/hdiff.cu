@@ -26,6 +26,9 @@
 // no block-wide barrier in either kernel.  HBM traffic is the algorithmic
 // minimum plus the 4 rows per march segment that two segments both read.
 #include <cstdlib>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -185,7 +188,8 @@ constexpr int kHaloBytes = 32;
 constexpr int kHaloPitchEdge = 128;
 __host__ __device__ constexpr int stage_bytes(int rows) { return rows * (2 * kRowBytes + kHaloPitchEdge); }
 __host__ __device__ constexpr int stage_tx_bytes(int rows) { return rows * (2 * kRowBytes + kHaloBytes); }
-__host__ __device__ constexpr int smem_bytes(int rows, int stages) { return stages * stage_bytes(rows) + 2 * stages * 8; }
+// ring + full/empty barriers + per-stage piece headers (persistent kernel)
+__host__ __device__ constexpr int smem_bytes(int rows, int stages) { return stages * stage_bytes(rows) + 2 * stages * 8 + stages * 4 + 8; }
 }  // namespace tmacfg
 
 template <class T, int VEC>
@@ -420,22 +424,265 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
   }
 }
 
-// SB200_HDIFF_CFG="variant,jt,hint_mode,pipeline,tail": variant 0 = auto, 1 = jmarch, 2 = tma;
-// jt = rows per CTA (0 = auto); tail = levels swept with short segments at the end of the launch
-// (0 = auto, -1 = none)
+// ---------------------------------------------------------------------------------
+// Persistent TMA kernel
+// ---------------------------------------------------------------------------------
+// Same CTA shape, same ring, same arithmetic as hdiff_tma_kernel, but the grid is as many CTAs as
+// the GPU keeps resident and every CTA sweeps piece after piece -- (i tile, segment of jt rows,
+// level), i tile fastest -- through ONE continuous TMA ring: the producer runs ahead into the next
+// piece while the consumers finish the current one, barriers are initialised once, no CTA is
+// launched or torn down during the sweep.  Pieces are handed out dynamically (the producer lane
+// draws the next one from a global counter and names it in the header of the ring stage that
+// carries its first rows), because SMs do not progress at the same speed: with a static
+// round-robin assignment the slowest CTA sets the time of the sweep (measured 1.47 ms against
+// 1.20 ms for hdiff_tma_kernel, whose CTAs the hardware hands out dynamically;
+// profiles/hdiff_persist_r02.log).
+struct HdiffSchedule {
+  int dynamic;        // 0: piece c, c + G, ... (static); 1: pieces from the counter
+  int xtiles;
+  int segments, jt;
+  int total;          // pieces = xtiles * segments * levels
+};
+
+struct HdiffPiece {
+  int xt, k, jb, je;
+};
+
+__device__ __forceinline__ HdiffPiece hdiff_piece(const HdiffSchedule& s, int w, int ny) {
+  HdiffPiece p;
+  p.xt = w % s.xtiles;
+  w /= s.xtiles;
+  p.k = w / s.segments;
+  p.jb = (w - p.k * s.segments) * s.jt;
+  p.je = min(p.jb + s.jt, ny);
+  return p;
+}
+
+template <class T, int R, int S, bool PEER>
+__global__ void __launch_bounds__(tmacfg::kThreads, 3)
+    hdiff_tma_persistent_kernel(const __grid_constant__ CUtensorMap map_inp,
+                                const __grid_constant__ CUtensorMap map_halo,
+                                const __grid_constant__ CUtensorMap map_coeff,
+                                const __grid_constant__ PeerMaps peer, T* __restrict__ out,
+                                unsigned int* __restrict__ counter, int nx, int ny,
+                                const HdiffSchedule sched, int64_t sy, int64_t sz) {
+  constexpr int VEC = VecN<T>::value;
+  constexpr int TW = tmacfg::kConsumers * VEC;
+  constexpr int STAGE = tmacfg::stage_bytes(R);
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE);
+  uint64_t* empty = full + S;
+  int* header = reinterpret_cast<int*>(empty + S);  // piece carried by a stage (its first stage only)
+  const int warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], tmacfg::kConsumers / 32);
+    }
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+
+  int slot = 0;
+  uint32_t phase = 0;  // parity of the ring round the next stage belongs to
+
+  if (warp == tmacfg::kConsumers / 32) {
+    // ===== producer warp: one lane drives the TMA ring through all pieces =====
+    if ((threadIdx.x & 31) == 0) {
+      tma::prefetch_tensormap(&map_inp);
+      tma::prefetch_tensormap(&map_halo);
+      tma::prefetch_tensormap(&map_coeff);
+      if (PEER) {
+        for (int w = 0; w < 3; ++w) {
+          tma::prefetch_tensormap(&peer.row_inp[w]);
+          tma::prefetch_tensormap(&peer.row_halo[w]);
+        }
+      }
+      bool first_round = true;
+      int next_static = int(blockIdx.x);
+      for (;;) {
+        int w;
+        if (sched.dynamic) {
+          w = int(atomicAdd(counter, 1u));
+        } else {
+          w = next_static;
+          next_static += int(gridDim.x);
+        }
+        if (w >= sched.total) {
+          // end marker: a stage without data whose header says so
+          if (!first_round) tma::mbar_wait(&empty[slot], phase ^ 1);
+          header[slot] = -1;
+          tma::mbar_arrive(&full[slot]);
+          break;
+        }
+        const HdiffPiece p = hdiff_piece(sched, w, ny);
+        const int c0 = p.xt * TW / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
+        const int nstages = (p.je - p.jb + 4 + R - 1) / R;  // rows jb-2 .. je+1
+        for (int n = 0; n < nstages; ++n) {
+          if (!first_round) tma::mbar_wait(&empty[slot], phase ^ 1);
+          unsigned char* stage = smem + slot * STAGE;
+          if (n == 0) header[slot] = w;
+          // stage n of a piece completes the output rows jb-4+nR ...: the first stage completes
+          // nothing and carries no coeff tile
+          const bool with_coeff = (n + 1) * R > 4;
+          tma::mbar_arrive_expect_tx(&full[slot],
+                                     tmacfg::stage_tx_bytes(R) - (with_coeff ? 0 : R * tmacfg::kRowBytes));
+          const int q0 = p.jb - 2 + n * R;  // first inp row of the stage
+          bool remote_rows = false;
+          if (PEER) remote_rows = (peer.has_lower && q0 < 0) || (peer.has_upper && q0 + R > ny);
+          if (PEER && remote_rows) {
+            // edge stage: row by row, each from the GPU that owns it
+            for (int r = 0; r < R; ++r) {
+              const int q = q0 + r;
+              int who = 0, row = q;
+              if (peer.has_lower && q < 0) {
+                who = 1;
+                row = peer.ny_lower + q;
+              } else if (peer.has_upper && q >= ny) {
+                who = 2;
+                row = q - ny;
+              }
+              tma::load_3d(stage + r * tmacfg::kRowBytes, &peer.row_inp[who], c0, row + 2, p.k, &full[slot]);
+              tma::load_3d(stage + 2 * R * tmacfg::kRowBytes + r * tmacfg::kHaloPitchEdge,
+                           &peer.row_halo[who], c0 + 256, row + 2, p.k, &full[slot]);
+            }
+          } else {
+            // tensor origins: inp at (i = -16 B, j = -2), coeff at (i = 0, j = 0)
+            tma::load_3d(stage, &map_inp, c0, q0 + 2, p.k, &full[slot]);
+            tma::load_3d(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, q0 + 2, p.k, &full[slot]);
+          }
+          if (with_coeff)
+            tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, q0 - 2, p.k, &full[slot]);
+          if (++slot == S) {
+            slot = 0;
+            phase ^= 1;
+            first_round = false;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const int t = threadIdx.x;
+  Strip<T, VEC> rc, rn, rnn;
+  T lc[VEC + 2], ln[VEC + 2], fym[VEC];
+#pragma unroll
+  for (int m = 0; m < VEC + 2; ++m) lc[m] = ln[m] = T(0);
+#pragma unroll
+  for (int n = 0; n < VEC; ++n) fym[n] = T(0);
+#pragma unroll
+  for (int n = 0; n < VEC + 4; ++n) rc.v[n] = rn.v[n] = T(0);
+
+  for (;;) {
+    // the stage that carries a piece's first rows names the piece
+    tma::mbar_wait(&full[slot], phase);
+    const int w = header[slot];
+    if (w < 0) break;
+    const HdiffPiece p = hdiff_piece(sched, w, ny);
+    const int i0 = p.xt * TW + t * VEC;
+    const bool active = i0 < nx;
+    const bool whole = i0 + VEC <= nx;
+    T* __restrict__ op = out + int64_t(p.k) * sz + i0;
+    const int nstages = (p.je - p.jb + 4 + R - 1) / R;
+    for (int n = 0; n < nstages; ++n) {
+      if (n > 0) tma::mbar_wait(&full[slot], phase);
+      const unsigned char* stage = smem + slot * STAGE;
+      int halo_pitch = tmacfg::kHaloBytes;
+      if (PEER) {
+        const int q0 = p.jb - 2 + n * R;
+        if ((peer.has_lower && q0 < 0) || (peer.has_upper && q0 + R > ny)) halo_pitch = tmacfg::kHaloPitchEdge;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int j = p.jb + n * R + r - 4;  // output row completed by inp row j + 2
+        read_strip<T, VEC>(stage + r * tmacfg::kRowBytes,
+                           stage + 2 * R * tmacfg::kRowBytes + r * halo_pitch, t, rnn);
+        T cf[VEC];
+        {
+          const unsigned char* c_row = stage + R * tmacfg::kRowBytes + r * tmacfg::kRowBytes + 16 * t;
+          if constexpr (sizeof(T) == 8) {
+            const double2 c = *reinterpret_cast<const double2*>(c_row);
+            cf[0] = c.x; cf[1] = c.y;
+          } else {
+            const float4 c = *reinterpret_cast<const float4*>(c_row);
+            cf[0] = c.x; cf[1] = c.y; cf[2] = c.z; cf[3] = c.w;
+          }
+        }
+        // rc = row j, rn = row j+1, rnn = row j+2; lc = lap(j), fym = fly(j-1).  The first four
+        // rows of a piece only refill this state (whatever the previous piece left in it is
+        // overwritten before row jb is completed); their results are never stored (j < jb).
+        laplacian<T, VEC>(rc, rn, rnn, ln);  // lap(j+1)
+        T flx[VEC + 1];
+#pragma unroll
+        for (int m = 0; m < VEC + 1; ++m)
+          flx[m] = limited(lc[m + 1] - lc[m], rc.v[m + 2] - rc.v[m + 1]);
+        T res[VEC];
+#pragma unroll
+        for (int m = 0; m < VEC; ++m) {
+          const T fy = limited(ln[m + 1] - lc[m + 1], rn.v[m + 2] - rc.v[m + 2]);
+          res[m] = rc.v[m + 2] - cf[m] * (flx[m + 1] - flx[m] + fy - fym[m]);
+          fym[m] = fy;
+        }
+        if (j >= p.jb && j < p.je && active) {
+          if (whole) {
+            store_vec<VEC, Cache::Streaming>(op + int64_t(j) * sy, res);
+          } else {
+#pragma unroll
+            for (int m = 0; m < VEC; ++m)
+              if (i0 + m < nx) op[int64_t(j) * sy + m] = res[m];
+          }
+        }
+        rc = rn;
+        rn = rnn;
+#pragma unroll
+        for (int m = 0; m < VEC + 2; ++m) lc[m] = ln[m];
+      }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) tma::mbar_arrive(&empty[slot]);
+      if (++slot == S) {
+        slot = 0;
+        phase ^= 1;
+      }
+    }
+  }
+}
+
+// SB200_HDIFF_CFG="variant,jt,hint_mode,pipeline,tail,persist,ctas_per_sm": variant 0 = auto,
+// 1 = jmarch, 2 = tma; jt = rows per segment (0 = auto); tail = levels swept with short segments at
+// the end of the launch (0 = auto, -1 = none); persist 0 = auto, 1 = one CTA per segment
+// (hdiff_tma_kernel), 2 = persistent CTAs drawing segments from a counter, 3 = persistent CTAs,
+// static round robin; ctas_per_sm = resident CTAs per SM of the persistent grid (0 = what fits)
 struct HdiffConfig {
   int variant = 0;
   int jt = 0;
   int hint_mode = 0;
   int pipeline = 0;
   int tail = 0;
+  int persist = 0;
+  int ctas_per_sm = 0;
 };
 
 inline HdiffConfig hdiff_config() {
   HdiffConfig cfg;
   if (const char* env = std::getenv("SB200_HDIFF_CFG"))
-    std::sscanf(env, "%d,%d,%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode, &cfg.pipeline, &cfg.tail);
+    std::sscanf(env, "%d,%d,%d,%d,%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode, &cfg.pipeline, &cfg.tail,
+                &cfg.persist, &cfg.ctas_per_sm);
   return cfg;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set once per (kernel, device)
+template <class Kernel>
+int ensure_dynamic_smem(Kernel kernel, int smem, std::atomic<uint64_t>& done) {
+  int device = 0;
+  SB200_CHECK(cudaGetDevice(&device));
+  const uint64_t bit = uint64_t(1) << (device & 63);
+  if (done.load(std::memory_order_acquire) & bit) return 0;
+  SB200_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  done.fetch_or(bit, std::memory_order_release);
+  return 0;
 }
 
 // Segments and regimes of one sweep (host only, no CUDA call unless a graded tail is requested).
@@ -509,16 +756,46 @@ inline bool hdiff_make_tiling(int R, int smem, int64_t xtiles, int64_t ny, int64
   return true;
 }
 
-template <class T, int R, int S>
-int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
-                     int64_t sy, int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
-                     cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
-                     int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
-                     int64_t sz_upper = 0) {
-  constexpr int VEC = VecN<T>::value;
-  constexpr int TW = tmacfg::kConsumers * VEC;
+// Tensor maps of one (fields, geometry) combination.  Encoding them is a handful of driver calls
+// (3 maps, 9 with neighbours); a time loop sweeps the same fields again and again, so they are
+// kept: the key is everything the maps depend on, the cache a small ring.
+struct HdiffMapsKey {
+  const void *inp, *coeff, *inp_lower, *inp_upper;
+  int64_t nx, ny, nz, sy, sz, ny_lower, sz_lower, ny_upper, sz_upper;
+  int element, rows, device;
+  bool operator==(const HdiffMapsKey& o) const {
+    return inp == o.inp && coeff == o.coeff && inp_lower == o.inp_lower && inp_upper == o.inp_upper &&
+           nx == o.nx && ny == o.ny && nz == o.nz && sy == o.sy && sz == o.sz && ny_lower == o.ny_lower &&
+           sz_lower == o.sz_lower && ny_upper == o.ny_upper && sz_upper == o.sz_upper &&
+           element == o.element && rows == o.rows && device == o.device;
+  }
+};
+struct HdiffMaps {
+  CUtensorMap inp, halo, coeff;
+  PeerMaps peer;
+};
+
+// 0 = encoded / found, 1 = error (reported), 2 = the TMA path does not apply to these fields
+template <class T, int R>
+int hdiff_maps(const T* inp, const T* coeff, int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz,
+               const T* inp_lower, int64_t ny_lower, int64_t sz_lower, const T* inp_upper, int64_t ny_upper,
+               int64_t sz_upper, HdiffMaps& maps) {
   constexpr int E = 8 / int(sizeof(T));  // data elements per 8-byte TMA element
-  *used = false;
+  constexpr int kEntries = 32;
+  static std::mutex mutex;
+  static std::vector<std::pair<HdiffMapsKey, HdiffMaps>> cache;
+  static size_t next = 0;
+  HdiffMapsKey key{inp, coeff, inp_lower, inp_upper, nx, ny, nz, sy, sz, ny_lower, sz_lower, ny_upper, sz_upper,
+                   int(sizeof(T)), R, 0};
+  if (cudaGetDevice(&key.device) != cudaSuccess) return fail("sb200_hdiff: no current device");
+  {
+    std::lock_guard<std::mutex> lock(mutex);
+    for (const auto& entry : cache)
+      if (entry.first == key) {
+        maps = entry.second;
+        return 0;
+      }
+  }
   // inp tensor: origin 16 bytes left of i = 0 and two rows below j = 0; extent covers
   // i in [-16 B, nx + 2), j in [-2, ny + 2)
   const T* inp_origin = inp - 16 / int(sizeof(T)) - 2 * sy;
@@ -527,62 +804,126 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
     // float32: the origin lies 2 elements outside a halo of width 2 and an odd nx rounds the
     // extent up by one element; only take the TMA path if that memory belongs to the allocation
     const T* last = inp_origin + (nz - 1) * sz + (ny + 3) * sy + inp_d0 * E;
-    if (!tma::range_is_allocated(inp_origin, last)) return 0;
+    if (!tma::range_is_allocated(inp_origin, last)) return 2;
   }
-  CUtensorMap map_inp, map_coeff;
-  if (!tma::encode_3d_u64(&map_inp, inp_origin, inp_d0, uint64_t(ny + 4), uint64_t(nz),
-                          uint64_t(sy) * sizeof(T), uint64_t(sz) * sizeof(T), 256, R, 1))
-    return 0;
-  if (!tma::encode_3d_u64(&map_coeff, coeff, uint64_t(ceil_div(nx, E)), uint64_t(ny), uint64_t(nz),
-                          uint64_t(sy) * sizeof(T), uint64_t(sz) * sizeof(T), 256, R, 1))
-    return 0;
+  const uint64_t bsy = uint64_t(sy) * sizeof(T), bsz = uint64_t(sz) * sizeof(T);
   // the right-halo box (4 x 8 bytes per row) needs its own descriptor: the box shape is part of it
-  CUtensorMap map_halo;
-  if (!tma::encode_3d_u64(&map_halo, inp_origin, inp_d0, uint64_t(ny + 4), uint64_t(nz),
-                          uint64_t(sy) * sizeof(T), uint64_t(sz) * sizeof(T), 4, R, 1))
-    return 0;
-
+  if (!tma::encode_3d_u64(&maps.inp, inp_origin, inp_d0, uint64_t(ny + 4), uint64_t(nz), bsy, bsz, 256, R, 1) ||
+      !tma::encode_3d_u64(&maps.coeff, coeff, uint64_t(ceil_div(nx, E)), uint64_t(ny), uint64_t(nz), bsy, bsz,
+                          256, R, 1) ||
+      !tma::encode_3d_u64(&maps.halo, inp_origin, inp_d0, uint64_t(ny + 4), uint64_t(nz), bsy, bsz, 4, R, 1))
+    return 2;
   // fused halo exchange: per-row maps on this slab and on the neighbours' slabs
-  const bool with_peers = inp_lower != nullptr || inp_upper != nullptr;
-  PeerMaps peer;
-  peer.ny_lower = int(ny_lower);
-  peer.has_lower = inp_lower != nullptr;
-  peer.has_upper = inp_upper != nullptr;
-  if (with_peers) {
+  maps.peer.ny_lower = int(ny_lower);
+  maps.peer.has_lower = inp_lower != nullptr;
+  maps.peer.has_upper = inp_upper != nullptr;
+  if (inp_lower != nullptr || inp_upper != nullptr) {
     const T* bases[3] = {inp, inp_lower ? inp_lower : inp, inp_upper ? inp_upper : inp};
     const int64_t rows[3] = {ny, inp_lower ? ny_lower : ny, inp_upper ? ny_upper : ny};
     // slabs with different row counts have different k strides
     const int64_t kstride[3] = {sz, inp_lower ? sz_lower : sz, inp_upper ? sz_upper : sz};
     for (int w = 0; w < 3; ++w) {
       const T* origin = bases[w] - 16 / int(sizeof(T)) - 2 * sy;
-      if (!tma::encode_3d_u64(&peer.row_inp[w], origin, inp_d0, uint64_t(rows[w] + 4), uint64_t(nz),
-                              uint64_t(sy) * sizeof(T), uint64_t(kstride[w]) * sizeof(T), 256, 1, 1) ||
-          !tma::encode_3d_u64(&peer.row_halo[w], origin, inp_d0, uint64_t(rows[w] + 4), uint64_t(nz),
-                              uint64_t(sy) * sizeof(T), uint64_t(kstride[w]) * sizeof(T), 4, 1, 1))
+      if (!tma::encode_3d_u64(&maps.peer.row_inp[w], origin, inp_d0, uint64_t(rows[w] + 4), uint64_t(nz), bsy,
+                              uint64_t(kstride[w]) * sizeof(T), 256, 1, 1) ||
+          !tma::encode_3d_u64(&maps.peer.row_halo[w], origin, inp_d0, uint64_t(rows[w] + 4), uint64_t(nz), bsy,
+                              uint64_t(kstride[w]) * sizeof(T), 4, 1, 1))
         return fail("sb200_hdiff_peer: cannot encode the tensor maps of the neighbouring slabs");
     }
   }
+  std::lock_guard<std::mutex> lock(mutex);
+  if (cache.size() < kEntries) {
+    cache.emplace_back(key, maps);
+  } else {
+    cache[next] = {key, maps};
+    next = (next + 1) % kEntries;
+  }
+  return 0;
+}
 
+template <class T, int R, int S>
+int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
+                     int64_t sy, int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
+                     cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
+                     int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
+                     int64_t sz_upper = 0) {
+  constexpr int VEC = VecN<T>::value;
+  constexpr int TW = tmacfg::kConsumers * VEC;
+  *used = false;
+  HdiffMaps maps;
+  const int status = hdiff_maps<T, R>(inp, coeff, nx, ny, nz, sy, sz, inp_lower, ny_lower, sz_lower, inp_upper,
+                                      ny_upper, sz_upper, maps);
+  if (status == 2) return 0;
+  if (status != 0) return status;
+  const bool with_peers = inp_lower != nullptr || inp_upper != nullptr;
   const int64_t xtiles = ceil_div(nx, TW);
   constexpr int smem = tmacfg::smem_bytes(R, S);
+  const HdiffConfig cfg = hdiff_config();
+
+  if (cfg.persist != 1) {
+    // persistent CTAs, one continuous ring each
+    static std::atomic<uint64_t> attr_local{0}, attr_peer{0};
+    static std::atomic<int> resident{0};
+    if (ensure_dynamic_smem(hdiff_tma_persistent_kernel<T, R, S, false>, smem, attr_local) ||
+        ensure_dynamic_smem(hdiff_tma_persistent_kernel<T, R, S, true>, smem, attr_peer))
+      return 1;
+    int per_sm = resident.load(std::memory_order_relaxed);
+    if (per_sm == 0) {
+      SB200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &per_sm, hdiff_tma_persistent_kernel<T, R, S, true>, tmacfg::kThreads, smem));
+      if (per_sm < 1) return fail("sb200_hdiff: the persistent kernel does not fit on this device");
+      resident.store(per_sm, std::memory_order_relaxed);
+    }
+    if (cfg.ctas_per_sm > 0) per_sm = std::min(per_sm, cfg.ctas_per_sm);
+    HdiffSchedule sched;
+    sched.dynamic = cfg.persist == 3 ? 0 : 1;
+    sched.xtiles = int(xtiles);
+    int jt = jt_request > 0 ? jt_request : 32;
+    jt = int(ceil_div(jt, R)) * R;
+    sched.jt = jt;
+    sched.segments = int(ceil_div(ny, jt));
+    const int64_t total = xtiles * sched.segments * nz;
+    if (total > 0x7fffff00) return fail("sb200_hdiff: domain too large for the launch grid");
+    sched.total = int(total);
+    const int64_t ctas = std::min<int64_t>(int64_t(sm_count()) * per_sm, total);
+    *used = true;
+    bool counter_ok = true;
+    auto launch = [&] {
+      unsigned int* counter = work_counter();
+      if (counter == nullptr || cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream) != cudaSuccess) {
+        counter_ok = false;
+        return;
+      }
+      if (with_peers)
+        hdiff_tma_persistent_kernel<T, R, S, true><<<unsigned(ctas), tmacfg::kThreads, smem, stream>>>(
+            maps.inp, maps.halo, maps.coeff, maps.peer, out, counter, int(nx), int(ny), sched, sy, sz);
+      else
+        hdiff_tma_persistent_kernel<T, R, S, false><<<unsigned(ctas), tmacfg::kThreads, smem, stream>>>(
+            maps.inp, maps.halo, maps.coeff, maps.peer, out, counter, int(nx), int(ny), sched, sy, sz);
+      count_launch();
+    };
+    const int rc = timed(launch, dry_runs, time, stream);
+    if (!counter_ok) return fail("sb200_hdiff: cannot allocate or reset the work counter");
+    return rc;
+  }
+
   HdiffTiling tiling;
   int64_t ctas_total = 0;
   if (!hdiff_make_tiling(R, smem, xtiles, ny, nz, jt_request, tiling, ctas_total))
     return fail("sb200_hdiff: domain too large for the launch grid");
   const dim3 grid{unsigned(ctas_total), 1, 1};
-  // per launch: the attribute is per device, and a process may drive several devices
-  SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S, false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  SB200_CHECK(cudaFuncSetAttribute(hdiff_tma_kernel<T, R, S, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static std::atomic<uint64_t> attr_local{0}, attr_peer{0};
+  if (ensure_dynamic_smem(hdiff_tma_kernel<T, R, S, false>, smem, attr_local) ||
+      ensure_dynamic_smem(hdiff_tma_kernel<T, R, S, true>, smem, attr_peer))
+    return 1;
   *used = true;
   auto launch = [&] {
     if (with_peers)
       hdiff_tma_kernel<T, R, S, true><<<grid, tmacfg::kThreads, smem, stream>>>(
-          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
+          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
     else
       hdiff_tma_kernel<T, R, S, false><<<grid, tmacfg::kThreads, smem, stream>>>(
-          map_inp, map_halo, map_coeff, peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
+          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);

@@ -8,6 +8,27 @@
 namespace sb200 {
 std::atomic<uint64_t> g_launches{0};
 
+// Work counters of the persistent kernels (dynamic scheduling): a small per-device pool, one
+// counter per launch in turn, zeroed by the caller on the launch's stream right before the kernel
+// (launches on different streams of one device may overlap; 64 of them in flight at once is more
+// than any caller here does).
+unsigned int* work_counter() {
+  constexpr int kDevices = 64, kPool = 64;
+  static std::mutex mutex;
+  static unsigned int* pool[kDevices] = {};
+  static unsigned next[kDevices] = {};
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= kDevices) return nullptr;
+  std::lock_guard<std::mutex> lock(mutex);
+  if (pool[device] == nullptr &&
+      cudaMalloc(reinterpret_cast<void**>(&pool[device]), kPool * sizeof(unsigned int)) != cudaSuccess) {
+    while (cudaGetLastError() != cudaSuccess) {
+    }
+    return nullptr;
+  }
+  return pool[device] + (next[device]++ % kPool);
+}
+
 namespace {
 __global__ void __launch_bounds__(256) flush_kernel(uint4* __restrict__ buffer, size_t n) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;

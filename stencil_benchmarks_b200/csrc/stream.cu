@@ -305,8 +305,16 @@ int check_array(const char* name, const T* x, size_t n, T expected, bool* ok) {
     return 0;
   }
   const double epsilon = sizeof(T) == 4 ? 1e-6 : 1e-13;
-  double* dsum;
-  unsigned long long* dbad;
+  double* dsum = nullptr;
+  unsigned long long* dbad = nullptr;
+  struct Scratch {  // freed on every path out of here
+    double*& sum;
+    unsigned long long*& bad;
+    ~Scratch() {
+      cudaFree(sum);
+      cudaFree(bad);
+    }
+  } scratch{dsum, dbad};
   SB200_CHECK(cudaMalloc(&dsum, sizeof(double)));
   SB200_CHECK(cudaMalloc(&dbad, sizeof(unsigned long long)));
   SB200_CHECK(cudaMemset(dsum, 0, sizeof(double)));
@@ -318,8 +326,6 @@ int check_array(const char* name, const T* x, size_t n, T expected, bool* ok) {
   unsigned long long bad;
   SB200_CHECK(cudaMemcpy(&sum, dsum, sizeof(double), cudaMemcpyDeviceToHost));
   SB200_CHECK(cudaMemcpy(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost));
-  SB200_CHECK(cudaFree(dsum));
-  SB200_CHECK(cudaFree(dbad));
   const double avg_err = sum / double(n);
   *ok = true;
   if (std::fabs(avg_err / double(expected)) > epsilon) {
@@ -354,9 +360,10 @@ int stream_run(uint64_t n, int ntimes, int verify) {
   SB200_CHECK(cudaDeviceSynchronize());
 
   const T scalar = 3;
-  cudaEvent_t start, stop;
-  SB200_CHECK(cudaEventCreate(&start));
-  SB200_CHECK(cudaEventCreate(&stop));
+  EventPair events;
+  SB200_CHECK(cudaEventCreate(&events.start));
+  SB200_CHECK(cudaEventCreate(&events.stop));
+  const cudaEvent_t start = events.start, stop = events.stop;
   std::vector<double> times[4];
   for (auto& t : times) t.resize(size_t(ntimes));
   const int ops[4] = {SB200_STREAM_COPY, SB200_STREAM_SCALE, SB200_STREAM_ADD, SB200_STREAM_TRIAD};
@@ -372,8 +379,6 @@ int stream_run(uint64_t n, int ntimes, int verify) {
       times[j][size_t(k)] = double(ms) / 1000.0;
     }
   }
-  SB200_CHECK(cudaEventDestroy(start));
-  SB200_CHECK(cudaEventDestroy(stop));
 
   const char* label[4] = {"Copy:      ", "Scale:     ", "Add:       ", "Triad:     "};
   const double bytes[4] = {2.0 * sizeof(T) * n, 2.0 * sizeof(T) * n, 3.0 * sizeof(T) * n,

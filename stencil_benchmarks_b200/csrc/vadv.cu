@@ -18,7 +18,9 @@
 // eliminated c and d to the ccol / dcol scratch fields; the backward sweep
 // reads them back.  HBM traffic: 5 reads + 2 writes forward, 3 reads + 1 write
 // backward.
+#include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -395,16 +397,32 @@ __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T
 }
 
 
+// Everything one launch needs about its components.  A launch solves `ncomp` = 1 or 3 systems:
+// component c reads its own ustage / upos / utens / utensstage fields and the shared wcon field
+// with the neighbour shift (ishift, jshift) = shifts[c] (u: i+1, v: j+1, w: none; base.py:475-483).
+struct VadvMaps {
+  CUtensorMap stage[3], pos[3], tens[3], tensstage[3];
+  CUtensorMap wcon, wcon_edge;
+};
+template <class T>
+struct VadvComponents {
+  T* tensstage[3];
+  int ishift[3], jshift[3];
+  int ncomp;
+  int two_wcon_tiles;  // some component has a j shift: ring stages carry a second wcon tile
+};
+
+// Work items are (batch, component) pairs, handed out dynamically: the producer lane draws the
+// next item from a global counter and passes it to the compute warps in the header of the ring
+// stage that carries the item's first chunk.  With three components the items of one batch are
+// drawn back to back, so three CTAs sweep the same columns at the same time and the wcon tiles
+// (and the j+1 tiles of the v component, which are the next row's own tiles) are fetched from HBM
+// once and hit the L2 twice: one launch moves 16 fields' worth of HBM traffic, not 18.
 template <class T, int KD>
 __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
-    vadv_onchip_kernel(const __grid_constant__ CUtensorMap map_stage,
-                       const __grid_constant__ CUtensorMap map_pos,
-                       const __grid_constant__ CUtensorMap map_tens,
-                       const __grid_constant__ CUtensorMap map_tensstage,
-                       const __grid_constant__ CUtensorMap map_wcon,
-                       const __grid_constant__ CUtensorMap map_wcon_edge, T* __restrict__ tensstage,
-                       int nx, int ny, int nz, int64_t sy, int64_t sz, int ishift, int jshift,
-                       int stages, int paired) {
+    vadv_onchip_kernel(const __grid_constant__ VadvMaps maps,
+                       const __grid_constant__ VadvComponents<T> comps, unsigned int* __restrict__ counter,
+                       int nx, int ny, int nz, int64_t sy, int64_t sz, int stages, int paired) {
   using C = VadvConst<T>;
   constexpr int COLS = vcfg::cols<T>();
   constexpr bool SPLIT = vcfg::split_wcon<T>();
@@ -413,22 +431,21 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
   constexpr int TILE = vcfg::tile_bytes<T>(KD);           // one field, KD levels
   constexpr int WB = vcfg::wcon_width<T>();                // wcon tile width in elements
   constexpr int WTILE = vcfg::wcon_tile_bytes<T>(KD);
-  const int STAGE = 4 * TILE + (jshift ? 2 : 1) * WTILE;
+  const int STAGE = 4 * TILE + (comps.two_wcon_tiles ? 2 : 1) * WTILE;
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: [ring: stages x STAGE][e store: (nz-1-paired) x COLS][barriers][tmem base]
+  // layout: [ring: stages x STAGE][e store: (nz-1-paired) x COLS][barriers][headers][tmem base]
   unsigned char* ring = smem;
   T* estore = reinterpret_cast<T*>(smem + stages * STAGE);
   uint64_t* full =
       reinterpret_cast<uint64_t*>(smem + stages * STAGE + size_t(nz - 1 - paired) * COLS * sizeof(T));
   uint64_t* empty = full + stages;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(empty + stages);
+  int* header = reinterpret_cast<int*>(empty + stages);  // item carried by a stage (first chunk only)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(header + stages);
 
   const int warp = threadIdx.x >> 5;
   const int nbx = (nx + COLS - 1) / COLS;
-  const int nbatches = nbx * ny;
+  const int nitems = nbx * ny * comps.ncomp;
   const int nchunks = (nz + KD - 1) / KD;
-  // batches of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-  const int my_batches = (nbatches - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -451,31 +468,44 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
   if (warp == COLS / 32) {
     // ===== producer warp =====
     if ((threadIdx.x & 31) == 0) {
-      tma::prefetch_tensormap(&map_stage);
-      tma::prefetch_tensormap(&map_pos);
-      tma::prefetch_tensormap(&map_tens);
-      tma::prefetch_tensormap(&map_tensstage);
-      tma::prefetch_tensormap(&map_wcon);
-      if (SPLIT) tma::prefetch_tensormap(&map_wcon_edge);
-      const uint32_t tx_bytes = 4 * TILE + vcfg::wcon_tx_bytes<T>(KD, true) +
-                                (jshift ? vcfg::wcon_tx_bytes<T>(KD, false) : 0);
+      for (int c = 0; c < comps.ncomp; ++c) {
+        tma::prefetch_tensormap(&maps.stage[c]);
+        tma::prefetch_tensormap(&maps.pos[c]);
+        tma::prefetch_tensormap(&maps.tens[c]);
+        tma::prefetch_tensormap(&maps.tensstage[c]);
+      }
+      tma::prefetch_tensormap(&maps.wcon);
+      if (SPLIT) tma::prefetch_tensormap(&maps.wcon_edge);
       int slot = 0, round = 0;  // ring position of the running chunk counter
-      for (int m = 0; m < my_batches; ++m) {
-        const int b = int(blockIdx.x) + m * int(gridDim.x);
+      for (;;) {
+        const int item = int(atomicAdd(counter, 1u));
+        if (item >= nitems) {
+          // end marker: a stage without data whose header says so
+          if (round > 0) tma::mbar_wait(&empty[slot], (round - 1) & 1);
+          header[slot] = -1;
+          tma::mbar_arrive(&full[slot]);
+          break;
+        }
+        const int comp = item % comps.ncomp;
+        const int b = item / comps.ncomp;
         const int j = b / nbx;
         const int it = (b - j * nbx) * COLS;
+        const int jshift = comps.jshift[comp];
+        const uint32_t tx_bytes = 4 * TILE + vcfg::wcon_tx_bytes<T>(KD, true) +
+                                  (jshift ? vcfg::wcon_tx_bytes<T>(KD, false) : 0);
         for (int c = 0; c < nchunks; ++c) {
           if (round > 0) tma::mbar_wait(&empty[slot], (round - 1) & 1);
           unsigned char* stage = ring + slot * STAGE;
+          if (c == 0) header[slot] = item;
           tma::mbar_arrive_expect_tx(&full[slot], tx_bytes);
           const int k0 = c * KD;
-          tma::load_3d(stage + 0 * TILE, &map_stage, it, j, k0, &full[slot]);
-          tma::load_3d(stage + 1 * TILE, &map_pos, it, j, k0, &full[slot]);
-          tma::load_3d(stage + 2 * TILE, &map_tens, it, j, k0, &full[slot]);
-          tma::load_3d(stage + 3 * TILE, &map_tensstage, it, j, k0, &full[slot]);
-          tma::load_3d(stage + 4 * TILE, &map_wcon, it, j, k0, &full[slot]);
-          if (SPLIT) tma::load_3d(stage + 4 * TILE + WMAIN, &map_wcon_edge, it + COLS, j, k0, &full[slot]);
-          if (jshift) tma::load_3d(stage + 4 * TILE + WTILE, &map_wcon, it, j + 1, k0, &full[slot]);
+          tma::load_3d(stage + 0 * TILE, &maps.stage[comp], it, j, k0, &full[slot]);
+          tma::load_3d(stage + 1 * TILE, &maps.pos[comp], it, j, k0, &full[slot]);
+          tma::load_3d(stage + 2 * TILE, &maps.tens[comp], it, j, k0, &full[slot]);
+          tma::load_3d(stage + 3 * TILE, &maps.tensstage[comp], it, j, k0, &full[slot]);
+          tma::load_3d(stage + 4 * TILE, &maps.wcon, it, j, k0, &full[slot]);
+          if (SPLIT) tma::load_3d(stage + 4 * TILE + WMAIN, &maps.wcon_edge, it + COLS, j, k0, &full[slot]);
+          if (jshift) tma::load_3d(stage + 4 * TILE + WTILE, &maps.wcon, it, j + 1, k0, &full[slot]);
           if (++slot == stages) {
             slot = 0;
             ++round;
@@ -495,10 +525,12 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
 
     VadvForward<T> f;
     T z = 0;                // backward state of the old column: x - pos of the level above
-    T* old_base = tensstage;
+    T* old_base = comps.tensstage[0];
     bool old_valid = false;
+    bool any_batch = false;
     int slot = 0, round = 0;
     int dir = 0;  // slot direction of the NEW column: level k -> slot (dir ? nz-2-k : k)
+    int ishift = 0, jshift = 0;  // neighbour shift of the running item's component
 
     // values of level r of the chunk in ring slot `slot`
     auto fetch = [&](const unsigned char* stage, int r, T& v_stage, T& v_pos, T& v_tens, T& v_tss,
@@ -531,19 +563,27 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
       }
     };
 
-    for (int m = 0; m < my_batches; ++m) {
-      const int b = int(blockIdx.x) + m * int(gridDim.x);
+    for (;;) {
+      // the stage that carries an item's first chunk names the item (the producer's end marker
+      // is a stage of its own)
+      tma::mbar_wait(&full[slot], round & 1);
+      const int item = header[slot];
+      if (item < 0) break;
+      any_batch = true;
+      const int comp = item % comps.ncomp;
+      const int b = item / comps.ncomp;
       const int j = b / nbx;
       const int i = (b - j * nbx) * COLS + t;
       const bool new_valid = i < nx;
-      T* new_base = tensstage + int64_t(j) * sy + i;
+      T* new_base = comps.tensstage[comp] + int64_t(j) * sy + i;
+      ishift = comps.ishift[comp];
+      jshift = comps.jshift[comp];
       // slot of the new column's level s-1 / the old column's level nz-1-s at step s
       const int p0 = dir ? nz - 1 : -1;
       const int dp = dir ? -1 : 1;  // slot(s) = p0 + dp * s
 
       // ---- first chunk, peeled: levels 0 and 1 are special ----
       {
-        tma::mbar_wait(&full[slot], round & 1);
         const unsigned char* stage = ring + slot * STAGE;
         T v_stage[KD], v_pos[KD], v_tens[KD], v_tss[KD], v_wsum[KD];
 #pragma unroll
@@ -623,7 +663,7 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
       dir ^= 1;
     }
     // ---- drain: backward sweep of the last column ----
-    if (my_batches > 0) {
+    if (any_batch) {
       const int p0 = dir ? nz - 1 : -1;
       const int dp = dir ? -1 : 1;
       for (int s = 1; s <= nz - 1; ++s) {
@@ -653,9 +693,16 @@ inline int vadv_variant_override() {
 }
 
 template <class T>
-int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage, const T* wcon,
-                       int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz, int ishift,
-                       int jshift, int dry_runs, double* time, cudaStream_t stream, bool* used) {
+struct VadvSystem {
+  const T *stage, *pos, *tens;
+  T* tensstage;
+  int ishift, jshift;
+};
+
+template <class T>
+int launch_vadv_onchip(const VadvSystem<T>* systems, int ncomp, const T* wcon, int64_t nx, int64_t ny,
+                       int64_t nz, int64_t sy, int64_t sz, int dry_runs, double* time, cudaStream_t stream,
+                       bool* used) {
   constexpr int KD = 4;
   constexpr int COLS = vcfg::cols<T>();
   *used = false;
@@ -668,6 +715,11 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
   if (const char* env = std::getenv("SB200_VADV_PAIRED")) paired = std::min(paired, std::atoi(env));
   int max_stages = 8;
   if (const char* env = std::getenv("SB200_VADV_STAGES")) max_stages = std::max(2, std::atoi(env));
+  int ishift = 0, jshift = 0;
+  for (int c = 0; c < ncomp; ++c) {
+    ishift = std::max(ishift, systems[c].ishift);
+    jshift = std::max(jshift, systems[c].jshift);
+  }
   // as many ring stages as fit next to the shared-memory part of the store (2 ... 8)
   const size_t stage_size = 4 * vcfg::tile_bytes<T>(KD) + (jshift ? 2 : 1) * vcfg::wcon_tile_bytes<T>(KD);
   const size_t fixed = size_t(slots - paired) * COLS * sizeof(T) + 256;
@@ -676,44 +728,73 @@ int launch_vadv_onchip(const T* stage, const T* pos, const T* tens, T* tensstage
   const size_t smem = stages * stage_size + fixed;
   const auto type = tma::tensor_type<T>();
   const uint64_t s1 = uint64_t(sy) * sizeof(T), s2 = uint64_t(sz) * sizeof(T);
-  CUtensorMap m_stage, m_pos, m_tens, m_tss, m_wcon, m_wcon_edge;
-  if (!tma::encode_3d(&m_stage, type, stage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
-      !tma::encode_3d(&m_pos, type, pos, nx, ny, nz, s1, s2, COLS, 1, KD) ||
-      !tma::encode_3d(&m_tens, type, tens, nx, ny, nz, s1, s2, COLS, 1, KD) ||
-      !tma::encode_3d(&m_tss, type, tensstage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
-      !tma::encode_3d(&m_wcon, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::wcon_width<T>(), 1, KD) ||
-      !tma::encode_3d(&m_wcon_edge, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::edge_elems<T>(), 1, KD))
+  VadvMaps maps;
+  VadvComponents<T> comps;
+  comps.ncomp = ncomp;
+  comps.two_wcon_tiles = jshift;
+  for (int c = 0; c < 3; ++c) {
+    const VadvSystem<T>& sys = systems[c < ncomp ? c : 0];
+    if (!tma::encode_3d(&maps.stage[c], type, sys.stage, nx, ny, nz, s1, s2, COLS, 1, KD) ||
+        !tma::encode_3d(&maps.pos[c], type, sys.pos, nx, ny, nz, s1, s2, COLS, 1, KD) ||
+        !tma::encode_3d(&maps.tens[c], type, sys.tens, nx, ny, nz, s1, s2, COLS, 1, KD) ||
+        !tma::encode_3d(&maps.tensstage[c], type, sys.tensstage, nx, ny, nz, s1, s2, COLS, 1, KD))
+      return 0;
+    comps.tensstage[c] = sys.tensstage;
+    comps.ishift[c] = sys.ishift;
+    comps.jshift[c] = sys.jshift;
+  }
+  // the wcon extent includes the neighbour column / row some component reads
+  if (!tma::encode_3d(&maps.wcon, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::wcon_width<T>(), 1, KD) ||
+      !tma::encode_3d(&maps.wcon_edge, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::edge_elems<T>(), 1,
+                      KD))
     return 0;
-  // per launch: the attribute is per device, and a process may drive several devices
-  SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  const int64_t nbatches = ceil_div(nx, COLS) * ny;
-  const unsigned grid = unsigned(std::min<int64_t>(nbatches, sm_count()));
+  static std::atomic<uint64_t> attr_done{0};
+  {
+    int device = 0;
+    SB200_CHECK(cudaGetDevice(&device));
+    const uint64_t bit = uint64_t(1) << (device & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+      SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+      attr_done.fetch_or(bit, std::memory_order_release);
+    }
+  }
+  const int64_t nitems = ceil_div(nx, COLS) * ny * ncomp;
+  if (nitems > 0x7fffff00) return fail("sb200_vadv: domain too large for the on-chip variant");
+  const unsigned grid = unsigned(std::min<int64_t>(nitems, sm_count()));
   *used = true;
+  bool counter_ok = true;
   auto launch = [&] {
+    unsigned int* counter = work_counter();
+    if (counter == nullptr || cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream) != cudaSuccess) {
+      counter_ok = false;
+      return;
+    }
     vadv_onchip_kernel<T, KD><<<grid, vcfg::threads<T>(), smem, stream>>>(
-        m_stage, m_pos, m_tens, m_tss, m_wcon, m_wcon_edge, tensstage, int(nx), int(ny), int(nz), sy, sz, ishift, jshift,
-        stages, paired);
+        maps, comps, counter, int(nx), int(ny), int(nz), sy, sz, stages, paired);
     count_launch();
   };
-  return timed(launch, dry_runs, time, stream);
+  const int rc = timed(launch, dry_runs, time, stream);
+  if (!counter_ok) return fail("sb200_vadv: cannot allocate or reset the work counter");
+  return rc;
 }
 
 template <class T>
-int launch_vadv(const T* stage, const T* pos, const T* tens, T* tensstage, const T* wcon, T* ccol,
-                T* dcol, int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz, int ishift,
-                int jshift, int variant, int dry_runs, double* time, cudaStream_t stream) {
+int launch_vadv(const VadvSystem<T>* systems, int ncomp, const T* wcon, T* ccol, T* dcol, int64_t nx,
+                int64_t ny, int64_t nz, int64_t sy, int64_t sz, int variant, int dry_runs, double* time,
+                cudaStream_t stream) {
   if (const int forced = vadv_variant_override()) variant = forced;
   constexpr int V = VecN<T>::value;
-  const bool aligned = aligned_to(stage, 16) && aligned_to(pos, 16) && aligned_to(tens, 16) &&
-                       aligned_to(tensstage, 16) && aligned_to(wcon, 16) && sy % V == 0 && sz % V == 0;
+  bool aligned = aligned_to(wcon, 16) && sy % V == 0 && sz % V == 0;
+  for (int c = 0; c < ncomp; ++c)
+    aligned = aligned && aligned_to(systems[c].stage, 16) && aligned_to(systems[c].pos, 16) &&
+              aligned_to(systems[c].tens, 16) && aligned_to(systems[c].tensstage, 16);
   if (variant != SB200_VADV_GLOBAL) {
     // the on-chip variant pays off once most of a 128-column batch is populated
     const bool wanted = variant == SB200_VADV_ONCHIP || nx >= 64;
     bool used = false;
     if (aligned && wanted) {
-      const int rc = launch_vadv_onchip<T>(stage, pos, tens, tensstage, wcon, nx, ny, nz, sy, sz, ishift,
-                                           jshift, dry_runs, time, stream, &used);
+      const int rc = launch_vadv_onchip<T>(systems, ncomp, wcon, nx, ny, nz, sy, sz, dry_runs, time, stream, &used);
       if (used || rc != 0) return rc;
     }
     if (variant == SB200_VADV_ONCHIP)
@@ -726,13 +807,30 @@ int launch_vadv(const T* stage, const T* pos, const T* tens, T* tensstage, const
   const dim3 block(bx, 1, 1);
   const dim3 grid(unsigned(ceil_div(nx, bx)), unsigned(ny), 1);
   if (grid.y > 65535u) return fail("sb200_vadv: domain too large for the launch grid");
-  const int64_t wshift = int64_t(ishift) + int64_t(jshift) * sy;
+  // the components share the ccol / dcol scratch fields: one sweep after the other
   auto launch = [&] {
-    vadv_global_kernel<T><<<grid, block, 0, stream>>>(stage, pos, tens, tensstage, wcon, ccol, dcol,
-                                                      int(nx), int(ny), int(nz), sy, sz, wshift);
-    count_launch();
+    for (int c = 0; c < ncomp; ++c) {
+      const VadvSystem<T>& sys = systems[c];
+      const int64_t wshift = int64_t(sys.ishift) + int64_t(sys.jshift) * sy;
+      vadv_global_kernel<T><<<grid, block, 0, stream>>>(sys.stage, sys.pos, sys.tens, sys.tensstage, wcon, ccol,
+                                                        dcol, int(nx), int(ny), int(nz), sy, sz, wshift);
+      count_launch();
+    }
   };
   return timed(launch, dry_runs, time, stream);
+}
+
+template <class T>
+int vadv_entry(int ncomp, const void* const* ustage, const void* const* upos, const void* const* utens,
+               void* const* utensstage, const int* ishift, const int* jshift, const void* wcon, void* ccol,
+               void* dcol, int64_t nx, int64_t ny, int64_t nz, int64_t sy, int64_t sz, int variant, int dry_runs,
+               double* time, cudaStream_t stream) {
+  VadvSystem<T> systems[3];
+  for (int c = 0; c < ncomp; ++c)
+    systems[c] = {static_cast<const T*>(ustage[c]), static_cast<const T*>(upos[c]), static_cast<const T*>(utens[c]),
+                  static_cast<T*>(utensstage[c]), ishift[c], jshift[c]};
+  return launch_vadv<T>(systems, ncomp, static_cast<const T*>(wcon), static_cast<T*>(ccol), static_cast<T*>(dcol),
+                        nx, ny, nz, sy, sz, variant, dry_runs, time, stream);
 }
 
 }  // namespace
@@ -740,28 +838,38 @@ int launch_vadv(const T* stage, const T* pos, const T* tens, T* tensstage, const
 
 using namespace sb200;
 
+extern "C" int sb200_vadv_components(int dtype, int ncomp, const void* const* ustage,
+                                     const void* const* upos, const void* const* utens,
+                                     void* const* utensstage, const int* ishift, const int* jshift,
+                                     const void* wcon, void* ccol, void* dcol, int64_t nx, int64_t ny,
+                                     int64_t nz, int64_t sx, int64_t sy, int64_t sz, int variant,
+                                     int dry_runs, double* time, void* stream) {
+  if (ncomp < 1 || ncomp > 3) return fail("sb200_vadv: between one and three components per launch");
+  if (ustage == nullptr || upos == nullptr || utens == nullptr || utensstage == nullptr || ishift == nullptr ||
+      jshift == nullptr)
+    return fail("sb200_vadv: null component table");
+  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sb200_vadv: domain must be positive");
+  if (nz < 2) return fail("sb200_vadv: at least two vertical levels are required");
+  if (sx != 1) return fail("sb200_vadv: only layout (2,1,0) is supported (unit stride along i)");
+  for (int c = 0; c < ncomp; ++c)
+    if (ishift[c] < 0 || ishift[c] > 1 || jshift[c] < 0 || jshift[c] > 1)
+      return fail("sb200_vadv: shifts must be 0 or 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == SB200_F64)
+    return vadv_entry<double>(ncomp, ustage, upos, utens, utensstage, ishift, jshift, wcon, ccol, dcol, nx, ny, nz,
+                              sy, sz, variant, dry_runs, time, s);
+  if (dtype == SB200_F32)
+    return vadv_entry<float>(ncomp, ustage, upos, utens, utensstage, ishift, jshift, wcon, ccol, dcol, nx, ny, nz,
+                             sy, sz, variant, dry_runs, time, s);
+  return fail("sb200_vadv: unsupported dtype");
+}
+
 extern "C" int sb200_vadv(int dtype, const void* ustage, const void* upos, const void* utens,
                           void* utensstage, const void* wcon, void* ccol, void* dcol, void* datacol,
                           int64_t nx, int64_t ny, int64_t nz, int64_t sx, int64_t sy, int64_t sz,
                           int ishift, int jshift, int variant, int dry_runs, double* time,
                           void* stream) {
   (void)datacol;
-  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sb200_vadv: domain must be positive");
-  if (nz < 2) return fail("sb200_vadv: at least two vertical levels are required");
-  if (sx != 1) return fail("sb200_vadv: only layout (2,1,0) is supported (unit stride along i)");
-  if (ishift < 0 || ishift > 1 || jshift < 0 || jshift > 1) return fail("sb200_vadv: shifts must be 0 or 1");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == SB200_F64)
-    return launch_vadv<double>(static_cast<const double*>(ustage), static_cast<const double*>(upos),
-                               static_cast<const double*>(utens), static_cast<double*>(utensstage),
-                               static_cast<const double*>(wcon), static_cast<double*>(ccol),
-                               static_cast<double*>(dcol), nx, ny, nz, sy, sz, ishift, jshift,
-                               variant, dry_runs, time, s);
-  if (dtype == SB200_F32)
-    return launch_vadv<float>(static_cast<const float*>(ustage), static_cast<const float*>(upos),
-                              static_cast<const float*>(utens), static_cast<float*>(utensstage),
-                              static_cast<const float*>(wcon), static_cast<float*>(ccol),
-                              static_cast<float*>(dcol), nx, ny, nz, sy, sz, ishift, jshift, variant,
-                              dry_runs, time, s);
-  return fail("sb200_vadv: unsupported dtype");
+  return sb200_vadv_components(dtype, 1, &ustage, &upos, &utens, &utensstage, &ishift, &jshift, wcon, ccol, dcol,
+                               nx, ny, nz, sx, sy, sz, variant, dry_runs, time, stream);
 }

@@ -12,6 +12,7 @@ min are reported with the algorithmic bytes of SURVEY.md §8d.
 import argparse
 import ctypes
 import json
+import os
 import statistics
 
 import numpy as np
@@ -57,8 +58,33 @@ def time_call(call, repeat):
     return statistics.median(times), min(times)
 
 
+def time_loop(lib, enqueue, steps, warmup=5):
+    """Mean time of `steps` back-to-back launches between two events (what bench.py measures)."""
+    start, stop = _vp(), _vp()
+    lib.sb200_event_create(ctypes.byref(start))
+    lib.sb200_event_create(ctypes.byref(stop))
+    for _ in range(warmup):
+        enqueue()
+    lib.sb200_synchronize(None)
+    lib.sb200_event_record(start, None)
+    for _ in range(steps):
+        enqueue()
+    lib.sb200_event_record(stop, None)
+    lib.sb200_synchronize(None)
+    elapsed = ctypes.c_double()
+    lib.sb200_event_elapsed(start, stop, ctypes.byref(elapsed))
+    lib.sb200_event_destroy(start)
+    lib.sb200_event_destroy(stop)
+    return elapsed.value / steps
+
+
 def main():
     parser = argparse.ArgumentParser()
+    parser.add_argument("--hdiff-sweep", default=None,
+                        help="semicolon-separated SB200_HDIFF_CFG values to time on the same fields")
+    parser.add_argument("--vadv-sweep", default=None,
+                        help="semicolon-separated NAME=VALUE[,NAME=VALUE] environment settings")
+    parser.add_argument("--loop", type=int, default=0, help="also time a loop of this many launches")
     parser.add_argument("--what", default="stream,basic,hdiff,vadv")
     parser.add_argument("--repeat", type=int, default=20)
     parser.add_argument("--out", default=None)
@@ -117,6 +143,20 @@ def main():
                 lambda t: lib.sb200_hdiff(code, _vp(f[0].interior), _vp(f[1].interior), _vp(f[2].interior),
                                           *domain, 1, sy, sz, 1, t, None), args.repeat)
             report("hdiff_2048x2048x80", dtype, nbytes, med, mn)
+            for cfg in (args.hdiff_sweep.split(";") if args.hdiff_sweep else []):
+                os.environ["SB200_HDIFF_CFG"] = cfg
+                med, mn = time_call(
+                    lambda t: lib.sb200_hdiff(code, _vp(f[0].interior), _vp(f[1].interior), _vp(f[2].interior),
+                                              *domain, 1, sy, sz, 1, t, None), args.repeat)
+                extra = {}
+                for steps in ([20, args.loop] if args.loop else []):
+                    extra[f"loop{steps}_ms"] = 1e3 * time_loop(
+                        lib, lambda: lib.sb200_hdiff(code, _vp(f[0].interior), _vp(f[1].interior),
+                                                     _vp(f[2].interior), *domain, 1, sy, sz, 0, None, None), steps)
+                report(f"hdiff cfg={cfg}", dtype, nbytes, med, mn, **extra)
+                if extra:
+                    print("    " + "  ".join(f"{k}={v:.4f}" for k, v in extra.items()), flush=True)
+            os.environ.pop("SB200_HDIFF_CFG", None)
             del f
         if "vadv" in what:
             domain, halo = (1024, 1024, 160), (3, 3, 3)
@@ -129,6 +169,32 @@ def main():
             report("vadv_1024x1024x160", dtype, nbytes, med, mn,
                    sbench_gbs=10 * int(np.prod(domain)) * size / med / 1e9)
             del f
+        if "vadv3" in what:
+            # all_components: u, v, w in one sweep sharing wcon (16 fields' worth of traffic)
+            domain, halo = (1024, 1024, 160), (3, 3, 3)
+            sy, sz, total, interior = padded_geometry(domain, halo, size)
+            comp = [[Field(total, interior, size, 0.1 + 0.1 * c + 0.02 * n) for n in range(4)] for c in range(3)]
+            wcon = Field(total, interior, size, 0.7)
+            nbytes = 16 * int(np.prod(domain)) * size
+
+            def table(n, count=3):
+                return (_vp * count)(*[_vp(comp[c][n].interior) for c in range(count)])
+
+            three = (ctypes.c_int * 3)
+            med, mn = time_call(
+                lambda t: lib.sb200_vadv_components(
+                    code, 3, table(0), table(1), table(2), table(3), three(1, 0, 0), three(0, 1, 0),
+                    _vp(wcon.interior), None, None, *domain, 1, sy, sz, capi.VADV_AUTO, 0, t, None), args.repeat)
+            report("vadv_uvw_merged_1024x1024x160", dtype, nbytes, med, mn)
+            total_med = 0.0
+            for c, (i, j) in enumerate([(1, 0), (0, 1), (0, 0)]):
+                med, mn = time_call(
+                    lambda t: lib.sb200_vadv(code, *[_vp(x.interior) for x in comp[c]], _vp(wcon.interior), None,
+                                             None, None, *domain, 1, sy, sz, i, j, capi.VADV_AUTO, 0, t, None),
+                    args.repeat)
+                total_med += med
+            report("vadv_uvw_three_sweeps", dtype, nbytes, total_med, total_med)
+            del comp, wcon
     if args.out:
         with open(args.out, "w") as fh:
             json.dump(dict(device=capi.device_info(), results=results), fh, indent=1)

@@ -108,8 +108,9 @@ def test_parameter_errors():
     with pytest.raises(benchmark.ParameterError, match="not divisible"):
         basic.Copy(alignment=12, **CPU)
     if not benchmark.HAVE_REFERENCE:
+        assert basic.Copy(pinned=False).verify is False  # stand-alone default: no oracle in the product
         with pytest.raises(benchmark.ParameterError, match="verify"):
-            basic.Copy(pinned=False)  # verify defaults to True and needs the reference's oracle
+            basic.Copy(pinned=False, verify=True)  # needs the reference's oracle
 
 
 @pytest.mark.parametrize("dtype,alignment", [("float64", 128), ("float32", 128), ("float64", 0)])
