@@ -182,13 +182,11 @@ int sb200_hdiff(int dtype, const void* inp, const void* coeff, void* out,
 
 /* Work decomposition sb200_hdiff uses for a domain on its TMA path (host only, no
  * device needed; no counterpart in the reference, whose block sizes are template
- * literals: cuda_hip/horizontal_diffusion.py:41).  CTA b of `*ctas` belongs to the
- * last regime r with b >= first_cta[r]; with c = b - first_cta[r] it sweeps i tile
- * c % *xtiles, rows [s*jt, min((s+1)*jt, ny)) with s = (c / *xtiles) % segments, on
- * level first_k[r] + c / (*xtiles * segments).  `table` receives 4 regimes x
- * {first_cta, first_k, segments, jt}; `*regimes` of them are in use. */
+ * literals: cuda_hip/horizontal_diffusion.py:41).  CTA b of `*ctas` sweeps i tile
+ * b % *xtiles, rows [s * *jt, min((s+1) * *jt, ny)) with s = (b / *xtiles) % *segments,
+ * on level b / (*xtiles * *segments). */
 int sb200_hdiff_tiling(int dtype, int64_t nx, int64_t ny, int64_t nz,
-                       int* xtiles, int* regimes, int* table, int64_t* ctas);
+                       int* xtiles, int* segments, int* jt, int64_t* ctas);
 
 /* Vertical advection, u component (oracle: sb/bc/stencils/base.py:349-501 with
  * all_components=False; reference GPU variants:

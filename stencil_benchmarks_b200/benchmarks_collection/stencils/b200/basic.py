@@ -22,7 +22,7 @@ class BasicStencilMixin(StencilMixin):
     def axis_and_mask(self):
         return 0, 0
 
-    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None):
+    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None, rows=None):
         axis, mask = self.axis_and_mask()
         self._lib.sb200_basic(
             self.kind, self._dtype_code, pointers["inp"], pointers["out"], *self.geometry(domain),

@@ -166,10 +166,18 @@ class StencilMixin(Benchmark):
         capi.synchronize(stream)
 
     # ---- the run protocol -------------------------------------------------------
-    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None):
+    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None, rows=None):
         """Call the stencil's C entry point; ``pointers`` maps field name -> interior void*;
-        ``domain`` overrides the swept domain (a j-slab of the fields)."""
+        ``domain`` overrides the swept domain (a j-slab of the fields, whose first row the pointers
+        address); ``rows`` = (first, last + 1) row of that slab inside the instance's domain."""
         raise NotImplementedError
+
+    # hooks of a J-partitioned instance (one slab of a global domain, see HorizontalDiffusionMixin)
+    def _before_sweeps(self, data, mirrors, stream):
+        """Called once per run before the first sweep is enqueued (``stream``: the upload stream)."""
+
+    def _after_sweeps(self):
+        """Called once per run after the last sweep has completed."""
 
     @property
     def algorithmic_bytes(self):
@@ -235,6 +243,7 @@ class StencilMixin(Benchmark):
         plane0, planes_in = hk - kr, nz + 2 * kr
         roles = [self.field_roles.get(name, "inout") for name in self.args]
         frontier = hy - jr  # first array row not yet uploaded
+        self._before_sweeps(data, mirrors, s_up)
         for c in range(self.chunks):
             j0, j1 = bounds[c], bounds[c + 1]
             if j1 == j0:
@@ -255,9 +264,10 @@ class StencilMixin(Benchmark):
                 for name, host in zip(self.args, data)
             }
             if self.dry_runs:
-                self.launch(pointers, self.dry_runs - 1, None, s_run.value, domain=(nx, j1 - j0, nz))
+                self.launch(pointers, self.dry_runs - 1, None, s_run.value, domain=(nx, j1 - j0, nz),
+                            rows=(j0, j1))
             check(raw.sb200_event_record(pipe["begin"][c], s_run))
-            self.launch(pointers, 0, None, s_run.value, domain=(nx, j1 - j0, nz))
+            self.launch(pointers, 0, None, s_run.value, domain=(nx, j1 - j0, nz), rows=(j0, j1))
             check(raw.sb200_event_record(pipe["end"][c], s_run))
             check(raw.sb200_stream_wait_event(s_down, pipe["end"][c]))
             for name, host, role in zip(self.args, data, roles):
@@ -268,6 +278,7 @@ class StencilMixin(Benchmark):
                         sz * size, (j1 - j0) * sy * size, nz, s_down))
         check(raw.sb200_synchronize(s_down))
         check(raw.sb200_synchronize(s_up))
+        self._after_sweeps()
         total = 0.0
         elapsed = ctypes.c_double()
         for c in range(self.chunks):
@@ -293,6 +304,7 @@ class StencilMixin(Benchmark):
             t0 = _time.perf_counter()
             if fresh or not self.resident:
                 self.upload(data, mirrors)
+            self._before_sweeps(data, mirrors, None)
             t1 = _time.perf_counter()
             pointers = {
                 name: self.interior_ptr(mirrors[name][1], host)
@@ -309,6 +321,7 @@ class StencilMixin(Benchmark):
                 self.launch(pointers, 0, None, None)
                 capi.synchronize()
                 elapsed.value = _time.perf_counter() - start
+            self._after_sweeps()
             t2 = _time.perf_counter()
             if self.verify or not self.resident:
                 self.download(data, mirrors)

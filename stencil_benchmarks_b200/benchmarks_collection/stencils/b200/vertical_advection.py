@@ -41,7 +41,7 @@ class VerticalAdvectionMixin(StencilMixin):
     def j_reach(self):
         return int(self.all_components)  # the v solve reads wcon(i, j+1)
 
-    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None):
+    def launch(self, pointers, dry_runs, time_ptr, stream, domain=None, rows=None):
         variant = {"auto": capi.VADV_AUTO, "global": capi.VADV_GLOBAL,
                    "onchip": capi.VADV_ONCHIP}[self.coefficients]
         components = [("u", 1, 0)]

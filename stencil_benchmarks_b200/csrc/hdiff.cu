@@ -188,8 +188,7 @@ constexpr int kHaloBytes = 32;
 constexpr int kHaloPitchEdge = 128;
 __host__ __device__ constexpr int stage_bytes(int rows) { return rows * (2 * kRowBytes + kHaloPitchEdge); }
 __host__ __device__ constexpr int stage_tx_bytes(int rows) { return rows * (2 * kRowBytes + kHaloBytes); }
-// ring + full/empty barriers + per-stage piece headers (persistent kernel)
-__host__ __device__ constexpr int smem_bytes(int rows, int stages) { return stages * stage_bytes(rows) + 2 * stages * 8 + stages * 4 + 8; }
+__host__ __device__ constexpr int smem_bytes(int rows, int stages) { return stages * stage_bytes(rows) + 2 * stages * 8; }
 }  // namespace tmacfg
 
 template <class T, int VEC>
@@ -226,18 +225,16 @@ struct PeerMaps {
 };
 
 // Work decomposition of one sweep: CTA = (256-wide i tile, segment of jt rows, level k), numbered
-// i-tile fastest, then segment, then level.  CTAs start in that order, so the last levels form the
-// tail of the launch, when SMs run dry one by one: the levels are split into regimes with shorter
-// and shorter segments, which makes the tail as long as a short CTA instead of a long one at the
-// price of re-reading 4 rows per short segment on the last levels.
+// i tile fastest, then segment, then level: the CTAs resident at any time sweep one compact band of
+// the field, and the eight i tiles of a segment, which together read whole rows, run side by side.
+// (Segments graded from long to short towards the end of the launch, persistent CTAs walking a
+// segment list through one continuous TMA ring -- with static and with dynamic assignment -- and L2
+// eviction hints on the TMA loads were all built and measured; none beats this:
+// profiles/hdiff_segments_r01.log, profiles/hdiff_persist_*_r02.log, profiles/hdiff_variants_r01.log.)
 struct HdiffTiling {
-  static constexpr int kMax = 4;
   int xtiles;
-  int regimes;            // 1 ... kMax, regime 0 first
-  int first_cta[kMax];    // linear index of a regime's first CTA
-  int first_k[kMax];      // its first level
-  int segments[kMax];     // segments per (i tile, level)
-  int jt[kMax];           // rows per segment
+  int segments;  // per (i tile, level)
+  int jt;        // rows per segment
 };
 
 template <class T, int R, int S, bool PEER>
@@ -246,7 +243,7 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
                      const __grid_constant__ CUtensorMap map_halo,
                      const __grid_constant__ CUtensorMap map_coeff,
                      const __grid_constant__ PeerMaps peer, T* __restrict__ out, int nx,
-                     int ny, const HdiffTiling tiling, int64_t sy, int64_t sz, int hint_mode) {
+                     int ny, const HdiffTiling tiling, int64_t sy, int64_t sz) {
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
   constexpr int STAGE = tmacfg::stage_bytes(R);
@@ -254,18 +251,13 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE);
   uint64_t* empty = full + S;
 
-  int b = int(blockIdx.x), regime = 0;
-#pragma unroll
-  for (int q = 1; q < HdiffTiling::kMax; ++q)
-    if (q < tiling.regimes && b >= tiling.first_cta[q]) regime = q;
-  b -= tiling.first_cta[regime];
-  const int segments = tiling.segments[regime], jt = tiling.jt[regime];
-  int k = tiling.first_k[regime];
+  int b = int(blockIdx.x);
   const int xt = b % tiling.xtiles;
   b /= tiling.xtiles;
-  k += b / segments;
+  const int k = b / tiling.segments;
+  const int jt = tiling.jt;
   const int it = xt * TW;  // first i of the tile
-  const int jb = (b % segments) * jt;
+  const int jb = (b - k * tiling.segments) * jt;
   const int je = min(jb + jt, ny);
   const int nstages = (je - jb + 4 + R - 1) / R;  // rows jb-2 .. je+1
   const int warp = threadIdx.x >> 5;
@@ -292,12 +284,6 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
         }
       }
       const int c0 = it / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
-      // Optional L2 policies (SB200_HDIFF_CFG third field): 1 = rows around a segment border
-      // evict_last, the rest evict_first; 2 = everything evict_first.  Both were measured and
-      // neither helps (profiles/hdiff_variants_r01.log: 1.286 / 1.238 ms vs 1.236 ms without
-      // hints), so the default is 0 = no hints.
-      const uint64_t keep = tma::policy_evict_last();
-      const uint64_t stream = tma::policy_evict_first();
       for (int n = 0; n < nstages; ++n) {
         const int slot = n % S;
         if (n >= S) tma::mbar_wait(&empty[slot], ((n / S) - 1) & 1);
@@ -330,19 +316,11 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
           }
           if (with_coeff)
             tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot]);
-        } else if (hint_mode == 0) {
+        } else {
           tma::load_3d(stage, &map_inp, c0, jb + n * R, k, &full[slot]);
           tma::load_3d(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, jb + n * R, k, &full[slot]);
           if (with_coeff)
             tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot]);
-        } else {
-          // rows jb-2 .. jb+1 (stage 0) and je-2 .. je+1 (last stage, possibly the one before) are shared
-          const bool border = hint_mode == 1 && (n == 0 || (n + 1) * R > je - jb);
-          const uint64_t policy = border ? keep : stream;
-          tma::load_3d_hint(stage, &map_inp, c0, jb + n * R, k, &full[slot], policy);
-          tma::load_3d_hint(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, jb + n * R, k, &full[slot], policy);
-          if (with_coeff)
-            tma::load_3d_hint(stage + R * tmacfg::kRowBytes, &map_coeff, c0, jb - 4 + n * R, k, &full[slot], stream);
         }
       }
     }
@@ -424,252 +402,18 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
   }
 }
 
-// ---------------------------------------------------------------------------------
-// Persistent TMA kernel
-// ---------------------------------------------------------------------------------
-// Same CTA shape, same ring, same arithmetic as hdiff_tma_kernel, but the grid is as many CTAs as
-// the GPU keeps resident and every CTA sweeps piece after piece -- (i tile, segment of jt rows,
-// level), i tile fastest -- through ONE continuous TMA ring: the producer runs ahead into the next
-// piece while the consumers finish the current one, barriers are initialised once, no CTA is
-// launched or torn down during the sweep.  Pieces are handed out dynamically (the producer lane
-// draws the next one from a global counter and names it in the header of the ring stage that
-// carries its first rows), because SMs do not progress at the same speed: with a static
-// round-robin assignment the slowest CTA sets the time of the sweep (measured 1.47 ms against
-// 1.20 ms for hdiff_tma_kernel, whose CTAs the hardware hands out dynamically;
-// profiles/hdiff_persist_r02.log).
-struct HdiffSchedule {
-  int dynamic;        // 0: piece c, c + G, ... (static); 1: pieces from the counter
-  int xtiles;
-  int segments, jt;
-  int total;          // pieces = xtiles * segments * levels
-};
-
-struct HdiffPiece {
-  int xt, k, jb, je;
-};
-
-__device__ __forceinline__ HdiffPiece hdiff_piece(const HdiffSchedule& s, int w, int ny) {
-  HdiffPiece p;
-  p.xt = w % s.xtiles;
-  w /= s.xtiles;
-  p.k = w / s.segments;
-  p.jb = (w - p.k * s.segments) * s.jt;
-  p.je = min(p.jb + s.jt, ny);
-  return p;
-}
-
-template <class T, int R, int S, bool PEER>
-__global__ void __launch_bounds__(tmacfg::kThreads, 3)
-    hdiff_tma_persistent_kernel(const __grid_constant__ CUtensorMap map_inp,
-                                const __grid_constant__ CUtensorMap map_halo,
-                                const __grid_constant__ CUtensorMap map_coeff,
-                                const __grid_constant__ PeerMaps peer, T* __restrict__ out,
-                                unsigned int* __restrict__ counter, int nx, int ny,
-                                const HdiffSchedule sched, int64_t sy, int64_t sz) {
-  constexpr int VEC = VecN<T>::value;
-  constexpr int TW = tmacfg::kConsumers * VEC;
-  constexpr int STAGE = tmacfg::stage_bytes(R);
-  extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE);
-  uint64_t* empty = full + S;
-  int* header = reinterpret_cast<int*>(empty + S);  // piece carried by a stage (its first stage only)
-  const int warp = threadIdx.x >> 5;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      tma::mbar_init(&full[s], 1);
-      tma::mbar_init(&empty[s], tmacfg::kConsumers / 32);
-    }
-    tma::fence_barrier_init();
-  }
-  __syncthreads();
-
-  int slot = 0;
-  uint32_t phase = 0;  // parity of the ring round the next stage belongs to
-
-  if (warp == tmacfg::kConsumers / 32) {
-    // ===== producer warp: one lane drives the TMA ring through all pieces =====
-    if ((threadIdx.x & 31) == 0) {
-      tma::prefetch_tensormap(&map_inp);
-      tma::prefetch_tensormap(&map_halo);
-      tma::prefetch_tensormap(&map_coeff);
-      if (PEER) {
-        for (int w = 0; w < 3; ++w) {
-          tma::prefetch_tensormap(&peer.row_inp[w]);
-          tma::prefetch_tensormap(&peer.row_halo[w]);
-        }
-      }
-      bool first_round = true;
-      int next_static = int(blockIdx.x);
-      for (;;) {
-        int w;
-        if (sched.dynamic) {
-          w = int(atomicAdd(counter, 1u));
-        } else {
-          w = next_static;
-          next_static += int(gridDim.x);
-        }
-        if (w >= sched.total) {
-          // end marker: a stage without data whose header says so
-          if (!first_round) tma::mbar_wait(&empty[slot], phase ^ 1);
-          header[slot] = -1;
-          tma::mbar_arrive(&full[slot]);
-          break;
-        }
-        const HdiffPiece p = hdiff_piece(sched, w, ny);
-        const int c0 = p.xt * TW / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
-        const int nstages = (p.je - p.jb + 4 + R - 1) / R;  // rows jb-2 .. je+1
-        for (int n = 0; n < nstages; ++n) {
-          if (!first_round) tma::mbar_wait(&empty[slot], phase ^ 1);
-          unsigned char* stage = smem + slot * STAGE;
-          if (n == 0) header[slot] = w;
-          // stage n of a piece completes the output rows jb-4+nR ...: the first stage completes
-          // nothing and carries no coeff tile
-          const bool with_coeff = (n + 1) * R > 4;
-          tma::mbar_arrive_expect_tx(&full[slot],
-                                     tmacfg::stage_tx_bytes(R) - (with_coeff ? 0 : R * tmacfg::kRowBytes));
-          const int q0 = p.jb - 2 + n * R;  // first inp row of the stage
-          bool remote_rows = false;
-          if (PEER) remote_rows = (peer.has_lower && q0 < 0) || (peer.has_upper && q0 + R > ny);
-          if (PEER && remote_rows) {
-            // edge stage: row by row, each from the GPU that owns it
-            for (int r = 0; r < R; ++r) {
-              const int q = q0 + r;
-              int who = 0, row = q;
-              if (peer.has_lower && q < 0) {
-                who = 1;
-                row = peer.ny_lower + q;
-              } else if (peer.has_upper && q >= ny) {
-                who = 2;
-                row = q - ny;
-              }
-              tma::load_3d(stage + r * tmacfg::kRowBytes, &peer.row_inp[who], c0, row + 2, p.k, &full[slot]);
-              tma::load_3d(stage + 2 * R * tmacfg::kRowBytes + r * tmacfg::kHaloPitchEdge,
-                           &peer.row_halo[who], c0 + 256, row + 2, p.k, &full[slot]);
-            }
-          } else {
-            // tensor origins: inp at (i = -16 B, j = -2), coeff at (i = 0, j = 0)
-            tma::load_3d(stage, &map_inp, c0, q0 + 2, p.k, &full[slot]);
-            tma::load_3d(stage + 2 * R * tmacfg::kRowBytes, &map_halo, c0 + 256, q0 + 2, p.k, &full[slot]);
-          }
-          if (with_coeff)
-            tma::load_3d(stage + R * tmacfg::kRowBytes, &map_coeff, c0, q0 - 2, p.k, &full[slot]);
-          if (++slot == S) {
-            slot = 0;
-            phase ^= 1;
-            first_round = false;
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumer warps =====
-  const int t = threadIdx.x;
-  Strip<T, VEC> rc, rn, rnn;
-  T lc[VEC + 2], ln[VEC + 2], fym[VEC];
-#pragma unroll
-  for (int m = 0; m < VEC + 2; ++m) lc[m] = ln[m] = T(0);
-#pragma unroll
-  for (int n = 0; n < VEC; ++n) fym[n] = T(0);
-#pragma unroll
-  for (int n = 0; n < VEC + 4; ++n) rc.v[n] = rn.v[n] = T(0);
-
-  for (;;) {
-    // the stage that carries a piece's first rows names the piece
-    tma::mbar_wait(&full[slot], phase);
-    const int w = header[slot];
-    if (w < 0) break;
-    const HdiffPiece p = hdiff_piece(sched, w, ny);
-    const int i0 = p.xt * TW + t * VEC;
-    const bool active = i0 < nx;
-    const bool whole = i0 + VEC <= nx;
-    T* __restrict__ op = out + int64_t(p.k) * sz + i0;
-    const int nstages = (p.je - p.jb + 4 + R - 1) / R;
-    for (int n = 0; n < nstages; ++n) {
-      if (n > 0) tma::mbar_wait(&full[slot], phase);
-      const unsigned char* stage = smem + slot * STAGE;
-      int halo_pitch = tmacfg::kHaloBytes;
-      if (PEER) {
-        const int q0 = p.jb - 2 + n * R;
-        if ((peer.has_lower && q0 < 0) || (peer.has_upper && q0 + R > ny)) halo_pitch = tmacfg::kHaloPitchEdge;
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int j = p.jb + n * R + r - 4;  // output row completed by inp row j + 2
-        read_strip<T, VEC>(stage + r * tmacfg::kRowBytes,
-                           stage + 2 * R * tmacfg::kRowBytes + r * halo_pitch, t, rnn);
-        T cf[VEC];
-        {
-          const unsigned char* c_row = stage + R * tmacfg::kRowBytes + r * tmacfg::kRowBytes + 16 * t;
-          if constexpr (sizeof(T) == 8) {
-            const double2 c = *reinterpret_cast<const double2*>(c_row);
-            cf[0] = c.x; cf[1] = c.y;
-          } else {
-            const float4 c = *reinterpret_cast<const float4*>(c_row);
-            cf[0] = c.x; cf[1] = c.y; cf[2] = c.z; cf[3] = c.w;
-          }
-        }
-        // rc = row j, rn = row j+1, rnn = row j+2; lc = lap(j), fym = fly(j-1).  The first four
-        // rows of a piece only refill this state (whatever the previous piece left in it is
-        // overwritten before row jb is completed); their results are never stored (j < jb).
-        laplacian<T, VEC>(rc, rn, rnn, ln);  // lap(j+1)
-        T flx[VEC + 1];
-#pragma unroll
-        for (int m = 0; m < VEC + 1; ++m)
-          flx[m] = limited(lc[m + 1] - lc[m], rc.v[m + 2] - rc.v[m + 1]);
-        T res[VEC];
-#pragma unroll
-        for (int m = 0; m < VEC; ++m) {
-          const T fy = limited(ln[m + 1] - lc[m + 1], rn.v[m + 2] - rc.v[m + 2]);
-          res[m] = rc.v[m + 2] - cf[m] * (flx[m + 1] - flx[m] + fy - fym[m]);
-          fym[m] = fy;
-        }
-        if (j >= p.jb && j < p.je && active) {
-          if (whole) {
-            store_vec<VEC, Cache::Streaming>(op + int64_t(j) * sy, res);
-          } else {
-#pragma unroll
-            for (int m = 0; m < VEC; ++m)
-              if (i0 + m < nx) op[int64_t(j) * sy + m] = res[m];
-          }
-        }
-        rc = rn;
-        rn = rnn;
-#pragma unroll
-        for (int m = 0; m < VEC + 2; ++m) lc[m] = ln[m];
-      }
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) tma::mbar_arrive(&empty[slot]);
-      if (++slot == S) {
-        slot = 0;
-        phase ^= 1;
-      }
-    }
-  }
-}
-
-// SB200_HDIFF_CFG="variant,jt,hint_mode,pipeline,tail,persist,ctas_per_sm": variant 0 = auto,
-// 1 = jmarch, 2 = tma; jt = rows per segment (0 = auto); tail = levels swept with short segments at
-// the end of the launch (0 = auto, -1 = none); persist 0 = auto, 1 = one CTA per segment
-// (hdiff_tma_kernel), 2 = persistent CTAs drawing segments from a counter, 3 = persistent CTAs,
-// static round robin; ctas_per_sm = resident CTAs per SM of the persistent grid (0 = what fits)
+// SB200_HDIFF_CFG="variant,jt,pipeline" (tuning aid): variant 0 = auto, 1 = jmarch, 2 = tma;
+// jt = rows per segment (0 = auto); pipeline = ring shape (see launch_hdiff_tma)
 struct HdiffConfig {
   int variant = 0;
   int jt = 0;
-  int hint_mode = 0;
   int pipeline = 0;
-  int tail = 0;
-  int persist = 0;
-  int ctas_per_sm = 0;
 };
 
 inline HdiffConfig hdiff_config() {
   HdiffConfig cfg;
   if (const char* env = std::getenv("SB200_HDIFF_CFG"))
-    std::sscanf(env, "%d,%d,%d,%d,%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.hint_mode, &cfg.pipeline, &cfg.tail,
-                &cfg.persist, &cfg.ctas_per_sm);
+    std::sscanf(env, "%d,%d,%d", &cfg.variant, &cfg.jt, &cfg.pipeline);
   return cfg;
 }
 
@@ -685,75 +429,26 @@ int ensure_dynamic_smem(Kernel kernel, int smem, std::atomic<uint64_t>& done) {
   return 0;
 }
 
-// Segments and regimes of one sweep (host only, no CUDA call unless a graded tail is requested).
-// R = rows per TMA stage, smem = dynamic shared memory per CTA.
-inline bool hdiff_make_tiling(int R, int smem, int64_t xtiles, int64_t ny, int64_t nz, int jt_request,
+// Segments of one sweep (host only).  R = rows per TMA stage.
+inline bool hdiff_make_tiling(int R, int64_t xtiles, int64_t ny, int64_t nz, int jt_request,
                               HdiffTiling& tiling, int64_t& ctas_total) {
   int jt = jt_request;
   if (jt <= 0) {
     // enough CTAs for ~8 per SM; otherwise 32-row segments.  Longer marches re-read fewer rows
     // (4 per segment, and those mostly hit L2 because neighbouring segments run concurrently) but
-    // measure slower: 128 rows 1.242 ms, 48: 1.229, 32: 1.196, 24: 1.175, 16: 1.167, 8: 1.519 for
-    // a single sweep; in a long loop under the board's power cap 32 rows is the fastest
-    // (1.222-1.228 vs 1.248 ms with 128, 1.250 with 24) -- profiles/hdiff_segments_r01.log
+    // measure slower: 128 rows 1.242 ms, 48: 1.229, 32: 1.196, 16: 1.167, 8: 1.519 for a single
+    // sweep; in a loop 32 rows is the fastest on every box seen (profiles/hdiff_segments_r01.log,
+    // profiles/hdiff_persist_dynamic_r02.log)
     const int64_t target = 148 * 8;
     int64_t segments = ceil_div(target, xtiles * nz);
     jt = int(std::min<int64_t>(32, std::max<int64_t>(16, ceil_div(ny, segments))));
   }
   jt = int(ceil_div(jt, R)) * R;
   tiling.xtiles = int(xtiles);
-  // regimes after the first: (rows per segment, levels), from SB200_HDIFF_TAIL="jt:levels,..."
-  // or, for requested segments of 64 rows and more, a default grading
-  int tail_jt[HdiffTiling::kMax - 1], tail_nz[HdiffTiling::kMax - 1], tails = 0;
-  const int mode = hdiff_config().tail;
-  if (const char* spec = std::getenv("SB200_HDIFF_TAIL")) {
-    while (tails < HdiffTiling::kMax - 1 && *spec) {
-      int a = 0, b = 0, used_chars = 0;
-      if (std::sscanf(spec, "%d:%d%n", &a, &b, &used_chars) != 2 || a <= 0 || b < 0) break;
-      tail_jt[tails] = int(ceil_div(a, R)) * R;
-      tail_nz[tails] = b;
-      ++tails;
-      spec += used_chars;
-      if (*spec == ',') ++spec;
-    }
-  } else if (mode >= 0 && jt >= 64) {
-    // about 1.5 waves of long CTAs' worth of work with quarter-length segments, at most half
-    // of the levels
-    const int64_t resident = int64_t(sm_count()) * std::min<int64_t>(4, (227 * 1024) / smem);
-    const int64_t per_level = xtiles * ceil_div(ny, jt);
-    tail_jt[0] = int(ceil_div(jt / 4, R)) * R;
-    tail_nz[0] = mode > 0 ? mode : int(std::min<int64_t>(nz / 2, ceil_div(3 * resident / 2, per_level)));
-    tails = 1;
-  }
-  int levels_left = int(nz);
-  for (int q = 0; q < tails; ++q) {
-    tail_nz[q] = std::min(tail_nz[q], levels_left);
-    levels_left -= tail_nz[q];
-  }
-  tiling.regimes = 0;
-  int64_t cta = 0;
-  int level = 0;
-  for (int q = 0; q <= tails; ++q) {
-    const int rows = q == 0 ? jt : tail_jt[q - 1];
-    const int levels = q == 0 ? levels_left : tail_nz[q - 1];
-    if (levels == 0) continue;
-    const int r = tiling.regimes++;
-    tiling.first_cta[r] = int(cta);
-    tiling.first_k[r] = level;
-    tiling.jt[r] = rows;
-    tiling.segments[r] = int(ceil_div(ny, rows));
-    cta += xtiles * tiling.segments[r] * levels;
-    level += levels;
-    if (cta > 0x7fffffff) return false;
-  }
-  for (int r = tiling.regimes; r < HdiffTiling::kMax; ++r) {
-    tiling.first_cta[r] = 0x7fffffff;
-    tiling.first_k[r] = 0;
-    tiling.segments[r] = 1;
-    tiling.jt[r] = R;
-  }
-  ctas_total = cta;
-  return true;
+  tiling.jt = jt;
+  tiling.segments = int(ceil_div(ny, jt));
+  ctas_total = xtiles * tiling.segments * nz;
+  return ctas_total <= 0x7fffffff;
 }
 
 // Tensor maps of one (fields, geometry) combination.  Encoding them is a handful of driver calls
@@ -843,7 +538,7 @@ int hdiff_maps(const T* inp, const T* coeff, int64_t nx, int64_t ny, int64_t nz,
 
 template <class T, int R, int S>
 int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz,
-                     int64_t sy, int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
+                     int64_t sy, int64_t sz, int jt_request, int dry_runs, double* time,
                      cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
                      int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
                      int64_t sz_upper = 0) {
@@ -858,58 +553,9 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
   const bool with_peers = inp_lower != nullptr || inp_upper != nullptr;
   const int64_t xtiles = ceil_div(nx, TW);
   constexpr int smem = tmacfg::smem_bytes(R, S);
-  const HdiffConfig cfg = hdiff_config();
-
-  if (cfg.persist != 1) {
-    // persistent CTAs, one continuous ring each
-    static std::atomic<uint64_t> attr_local{0}, attr_peer{0};
-    static std::atomic<int> resident{0};
-    if (ensure_dynamic_smem(hdiff_tma_persistent_kernel<T, R, S, false>, smem, attr_local) ||
-        ensure_dynamic_smem(hdiff_tma_persistent_kernel<T, R, S, true>, smem, attr_peer))
-      return 1;
-    int per_sm = resident.load(std::memory_order_relaxed);
-    if (per_sm == 0) {
-      SB200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &per_sm, hdiff_tma_persistent_kernel<T, R, S, true>, tmacfg::kThreads, smem));
-      if (per_sm < 1) return fail("sb200_hdiff: the persistent kernel does not fit on this device");
-      resident.store(per_sm, std::memory_order_relaxed);
-    }
-    if (cfg.ctas_per_sm > 0) per_sm = std::min(per_sm, cfg.ctas_per_sm);
-    HdiffSchedule sched;
-    sched.dynamic = cfg.persist == 3 ? 0 : 1;
-    sched.xtiles = int(xtiles);
-    int jt = jt_request > 0 ? jt_request : 32;
-    jt = int(ceil_div(jt, R)) * R;
-    sched.jt = jt;
-    sched.segments = int(ceil_div(ny, jt));
-    const int64_t total = xtiles * sched.segments * nz;
-    if (total > 0x7fffff00) return fail("sb200_hdiff: domain too large for the launch grid");
-    sched.total = int(total);
-    const int64_t ctas = std::min<int64_t>(int64_t(sm_count()) * per_sm, total);
-    *used = true;
-    bool counter_ok = true;
-    auto launch = [&] {
-      unsigned int* counter = work_counter();
-      if (counter == nullptr || cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream) != cudaSuccess) {
-        counter_ok = false;
-        return;
-      }
-      if (with_peers)
-        hdiff_tma_persistent_kernel<T, R, S, true><<<unsigned(ctas), tmacfg::kThreads, smem, stream>>>(
-            maps.inp, maps.halo, maps.coeff, maps.peer, out, counter, int(nx), int(ny), sched, sy, sz);
-      else
-        hdiff_tma_persistent_kernel<T, R, S, false><<<unsigned(ctas), tmacfg::kThreads, smem, stream>>>(
-            maps.inp, maps.halo, maps.coeff, maps.peer, out, counter, int(nx), int(ny), sched, sy, sz);
-      count_launch();
-    };
-    const int rc = timed(launch, dry_runs, time, stream);
-    if (!counter_ok) return fail("sb200_hdiff: cannot allocate or reset the work counter");
-    return rc;
-  }
-
   HdiffTiling tiling;
   int64_t ctas_total = 0;
-  if (!hdiff_make_tiling(R, smem, xtiles, ny, nz, jt_request, tiling, ctas_total))
+  if (!hdiff_make_tiling(R, xtiles, ny, nz, jt_request, tiling, ctas_total))
     return fail("sb200_hdiff: domain too large for the launch grid");
   const dim3 grid{unsigned(ctas_total), 1, 1};
   static std::atomic<uint64_t> attr_local{0}, attr_peer{0};
@@ -920,32 +566,29 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
   auto launch = [&] {
     if (with_peers)
       hdiff_tma_kernel<T, R, S, true><<<grid, tmacfg::kThreads, smem, stream>>>(
-          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
+          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz);
     else
       hdiff_tma_kernel<T, R, S, false><<<grid, tmacfg::kThreads, smem, stream>>>(
-          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz, hint_mode);
+          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz);
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);
 }
 
-// rows per stage x stages of the TMA ring; SB200_HDIFF_CFG fourth field selects an alternative
+// rows per stage x stages of the TMA ring; SB200_HDIFF_CFG's third field selects the alternative
 template <class T>
 int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, int64_t nz, int64_t sy,
-                     int64_t sz, int jt_request, int hint_mode, int dry_runs, double* time,
+                     int64_t sz, int jt_request, int dry_runs, double* time,
                      cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
                      int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
                      int64_t sz_upper = 0) {
 #define SB200_TMA_ARGS                                                                              \
-  inp, coeff, out, nx, ny, nz, sy, sz, jt_request, hint_mode, dry_runs, time, stream, used, inp_lower, \
+  inp, coeff, out, nx, ny, nz, sy, sz, jt_request, dry_runs, time, stream, used, inp_lower, \
       ny_lower, sz_lower, inp_upper, ny_upper, sz_upper
-  switch (hdiff_config().pipeline) {
-    case 1: return launch_hdiff_tma_rs<T, 4, 3>(SB200_TMA_ARGS);
-    case 2: return launch_hdiff_tma_rs<T, 8, 2>(SB200_TMA_ARGS);
-    case 3: return launch_hdiff_tma_rs<T, 8, 3>(SB200_TMA_ARGS);
-    case 4: return launch_hdiff_tma_rs<T, 2, 6>(SB200_TMA_ARGS);
-    default: return launch_hdiff_tma_rs<T, 4, 4>(SB200_TMA_ARGS);  // best of the sweep, by <1 %
-  }
+  // 4 rows x 4 stages is the best of the shapes measured (4x3, 8x2, 8x3, 2x6 are within 2.5 %:
+  // profiles/hdiff_variants_r01.log); 4x3 is kept as the alternative for tuning runs
+  if (hdiff_config().pipeline == 1) return launch_hdiff_tma_rs<T, 4, 3>(SB200_TMA_ARGS);
+  return launch_hdiff_tma_rs<T, 4, 4>(SB200_TMA_ARGS);
 #undef SB200_TMA_ARGS
 }
 
@@ -962,7 +605,7 @@ int launch_hdiff(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, i
   // (profiles/size_sweep_r01.log)
   if (vector_ok && cfg.variant != 1 && (cfg.variant == 2 || nx * int64_t(sizeof(T)) >= 512)) {
     bool used = false;
-    const int rc = launch_hdiff_tma<T>(inp, coeff, out, nx, ny, nz, sy, sz, cfg.jt, cfg.hint_mode, dry_runs,
+    const int rc = launch_hdiff_tma<T>(inp, coeff, out, nx, ny, nz, sy, sz, cfg.jt, dry_runs,
                                        time, stream, &used);
     if (used || rc != 0) return rc;
   }
@@ -1017,14 +660,14 @@ extern "C" int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, v
     if (sy % 2 || sz % 2 || sz_lower % 2 || sz_upper % 2)
       return fail("sb200_hdiff_peer: strides must keep rows 16-byte aligned");
     rc = launch_hdiff_tma<double>(static_cast<const double*>(inp), static_cast<const double*>(coeff),
-                                  static_cast<double*>(out), nx, ny, nz, sy, sz, cfg.jt, 0, dry_runs, time, s,
+                                  static_cast<double*>(out), nx, ny, nz, sy, sz, cfg.jt, dry_runs, time, s,
                                   &used, static_cast<const double*>(inp_lower), ny_lower, sz_lower,
                                   static_cast<const double*>(inp_upper), ny_upper, sz_upper);
   } else if (dtype == SB200_F32) {
     if (sy % 4 || sz % 4 || sz_lower % 4 || sz_upper % 4)
       return fail("sb200_hdiff_peer: strides must keep rows 16-byte aligned");
     rc = launch_hdiff_tma<float>(static_cast<const float*>(inp), static_cast<const float*>(coeff),
-                                 static_cast<float*>(out), nx, ny, nz, sy, sz, cfg.jt, 0, dry_runs, time, s,
+                                 static_cast<float*>(out), nx, ny, nz, sy, sz, cfg.jt, dry_runs, time, s,
                                  &used, static_cast<const float*>(inp_lower), ny_lower, sz_lower,
                                  static_cast<const float*>(inp_upper), ny_upper, sz_upper);
   } else {
@@ -1034,28 +677,21 @@ extern "C" int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, v
   return rc;
 }
 
-extern "C" int sb200_hdiff_tiling(int dtype, int64_t nx, int64_t ny, int64_t nz, int* xtiles, int* regimes,
-                                  int* table, int64_t* ctas) {
+extern "C" int sb200_hdiff_tiling(int dtype, int64_t nx, int64_t ny, int64_t nz, int* xtiles, int* segments,
+                                  int* jt, int64_t* ctas) {
   if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sb200_hdiff_tiling: domain must be positive");
   if (dtype != SB200_F64 && dtype != SB200_F32) return fail("sb200_hdiff_tiling: unsupported dtype");
-  if (xtiles == nullptr || regimes == nullptr || table == nullptr || ctas == nullptr)
+  if (xtiles == nullptr || segments == nullptr || jt == nullptr || ctas == nullptr)
     return fail("sb200_hdiff_tiling: null output pointer");
-  // the default ring: 4 rows per stage, 4 stages (launch_hdiff_tma)
-  constexpr int R = 4, S = 4;
+  constexpr int R = 4;  // rows per stage of the default ring (launch_hdiff_tma)
   const int tile_width = tmacfg::kConsumers * (dtype == SB200_F64 ? VecN<double>::value : VecN<float>::value);
   HdiffTiling tiling;
   int64_t total = 0;
-  if (!hdiff_make_tiling(R, tmacfg::smem_bytes(R, S), ceil_div(nx, tile_width), ny, nz, hdiff_config().jt, tiling,
-                         total))
+  if (!hdiff_make_tiling(R, ceil_div(nx, tile_width), ny, nz, hdiff_config().jt, tiling, total))
     return fail("sb200_hdiff_tiling: domain too large for the launch grid");
   *xtiles = tiling.xtiles;
-  *regimes = tiling.regimes;
-  for (int r = 0; r < HdiffTiling::kMax; ++r) {
-    table[4 * r + 0] = tiling.first_cta[r];
-    table[4 * r + 1] = tiling.first_k[r];
-    table[4 * r + 2] = tiling.segments[r];
-    table[4 * r + 3] = tiling.jt[r];
-  }
+  *segments = tiling.segments;
+  *jt = tiling.jt;
   *ctas = total;
   return 0;
 }

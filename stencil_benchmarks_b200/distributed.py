@@ -72,6 +72,12 @@ class HaloExchange:
                  make_buffer: Callable, pack: Callable, unpack: Callable, group=None):
         if width > ny:
             raise ValueError("halo wider than the local slab")
+        if world_size > 1:
+            # the neighbours send `width` rows of THEIR slabs: every slab must hold that many
+            counts = [None] * world_size
+            dist.all_gather_object(counts, int(ny), group=group)
+            if min(counts) < width:
+                raise ValueError(f"halo of width {width} wider than the smallest slab ({min(counts)} rows)")
         self.dist = dist
         self.rank, self.world_size = rank, world_size
         self.ny, self.width = ny, width
@@ -114,6 +120,34 @@ class HaloExchange:
             if buffer is not None:
                 total += buffer.numel() * buffer.element_size()
         return total
+
+
+def attach_neighbours(bench, dist, rank, world_size, group=None):
+    """Make a horizontal-diffusion instance the sweep of ONE J slab of a domain partitioned over
+    ``world_size`` ranks: map the neighbours' ``inp`` slabs (PeerSlabs) and hand them to the
+    instance, whose ``run()`` then reads its halo rows from the neighbours (one kernel per sweep)
+    and orders its copies against theirs.  Returns the PeerSlabs (close() it at the end)."""
+    data = bench.data(0)
+    mirrors = bench._device_fields(data)
+    interior = bench.interior_ptr(mirrors["inp"][1], data.inp).value
+    peers = PeerSlabs(dist, rank, world_size, mirrors["inp"][0].ptr, interior, int(bench.domain[1]),
+                      int(bench.strides[2]), group=group)
+    bench.peers = peers
+    return peers
+
+
+def global_rows(field_seed, rows, nx, nz, halo=(3, 3, 3), dtype="float64"):
+    """Rows ``rows`` (indices into the padded global array) of a synthetic global field
+    U[0,1) whose j-th row depends on (field_seed, j) only: every rank can build its own slab --
+    and the true halo rows around it -- without ever holding the global field.  Shape
+    (nx + 2 hx, len(rows), nz + 2 hz)."""
+    import numpy as np
+
+    width, levels = nx + 2 * halo[0], nz + 2 * halo[2]
+    out = np.empty((width, len(rows), levels), dtype=dtype)
+    for n, j in enumerate(rows):
+        out[:, n, :] = np.random.default_rng([field_seed, j]).random((levels, width)).T
+    return out
 
 
 def cuda_halo_exchange(rank, world_size, dtype, nx, ny, nz, hx, sy, sz, width, group=None):
@@ -165,6 +199,7 @@ class PeerSlabs:
         from . import capi
 
         self._lib = capi.library()
+        self._dist, self._group = dist, group
         handle = (ctypes.c_ubyte * 64)()
         self._lib.sb200_ipc_get_handle(ctypes.c_void_p(base_ptr), handle)
         mine = (bytes(handle), int(interior_ptr - base_ptr), int(ny), int(sz))
@@ -186,6 +221,14 @@ class PeerSlabs:
             setattr(self, who, mapped.value + offset)
             setattr(self, "ny_" + who, rows)
             setattr(self, "sz_" + who, kstride)
+
+    def barrier(self):
+        """All ranks of the partition have reached this point (host side).  Orders the uploads of
+        one rank against the sweeps of its neighbours: the fused exchange reads the neighbours'
+        ``inp`` rows straight from their HBM, so whenever ``inp`` changes between sweeps (a new
+        upload, a time loop that swaps fields) every rank has to pass a barrier -- or use the
+        in-kernel step flags of the iterated mode -- before the next sweep starts."""
+        self._dist.barrier(group=self._group)
 
     def close(self):
         for mapped in self._opened:

@@ -167,10 +167,15 @@ def test_reference_cli_runs_the_backend(tmp_path):
 
 
 def test_cli_exit_codes_follow_the_reference(tmp_path):
-    """Invalid parameters are skippable ParameterErrors (cli.py:53-61): `-s` skips them."""
-    result = run(CLI, tmp_path, "-s", "--executions", "1", "stencils", "b200", "horizontal-diffusion",
-                 "fused", "--domain", "16", "16", "4", "--layout", "0", "1", "2")
+    """Invalid parameters are skippable ParameterErrors (cli.py:53-61): with `-s` the int32 member
+    of the range is skipped and the float64 one runs."""
+    import pandas as pd
+
+    out = tmp_path / "skip.csv"
+    result = run(CLI, tmp_path, "-s", "--executions", "1", "--output", str(out), "stencils", "b200",
+                 "horizontal-diffusion", "fused", "--domain", "16", "16", "4", "--dtype", "[int32,float64]")
     assert result.returncode == 0, result.stdout + result.stderr
+    assert list(pd.read_csv(out)["dtype"]) == ["float64"]
 
 
 def test_collection_script_writes_the_reference_csv(tmp_path):

@@ -232,31 +232,27 @@ def _hdiff_tiles(dtype, domain):
     import ctypes
 
     lib = capi.library()
-    xtiles, regimes, ctas = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
-    table = (ctypes.c_int * 16)()
-    lib.sb200_hdiff_tiling(capi.dtype_code(dtype), *domain, ctypes.byref(xtiles), ctypes.byref(regimes),
-                           table, ctypes.byref(ctas))
-    first_cta, first_k, segments, jt = (np.array(table[i::4][:regimes.value]) for i in range(4))
+    xtiles, segments, jt, ctas = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+    lib.sb200_hdiff_tiling(capi.dtype_code(dtype), *domain, ctypes.byref(xtiles), ctypes.byref(segments),
+                           ctypes.byref(jt), ctypes.byref(ctas))
     b = np.arange(ctas.value)
-    regime = np.searchsorted(first_cta, b, side="right") - 1
-    c = b - first_cta[regime]
-    xt = c % xtiles.value
-    seg = (c // xtiles.value) % segments[regime]
-    k = first_k[regime] + c // (xtiles.value * segments[regime])
-    j0 = seg * jt[regime]
-    j1 = np.minimum(j0 + jt[regime], domain[1])
+    xt = b % xtiles.value
+    seg = (b // xtiles.value) % segments.value
+    k = b // (xtiles.value * segments.value)
+    j0 = seg * jt.value
+    j1 = np.minimum(j0 + jt.value, domain[1])
     return xtiles.value, xt, k, j0, j1
 
 
-@pytest.mark.parametrize("tail", [None, "64:3,32:2,16:1", "16:100", "8:1"])
+@pytest.mark.parametrize("cfg", [None, "0,64", "0,6", "0,2048"])
 @pytest.mark.parametrize("dtype,domain", [("float64", (2048, 2048, 80)), ("float64", (300, 67, 5)),
                                           ("float32", (1000, 33, 7)), ("float64", (64, 1, 1)),
                                           ("float32", (513, 4100, 2))])
-def test_hdiff_tiling_covers_every_row_once(monkeypatch, dtype, domain, tail):
-    """The work decomposition of the TMA kernel (uniform segments or graded regimes) is a partition:
-    every (i tile, level, row) belongs to exactly one CTA (include/sbench_b200.h: sb200_hdiff_tiling)."""
-    if tail is not None:
-        monkeypatch.setenv("SB200_HDIFF_TAIL", tail)
+def test_hdiff_tiling_covers_every_row_once(monkeypatch, dtype, domain, cfg):
+    """The work decomposition of the TMA kernel is a partition: every (i tile, level, row) belongs
+    to exactly one CTA (include/sbench_b200.h: sb200_hdiff_tiling)."""
+    if cfg is not None:
+        monkeypatch.setenv("SB200_HDIFF_CFG", cfg)
     nx, ny, nz = domain
     xtiles, xt, k, j0, j1 = _hdiff_tiles(dtype, domain)
     tile_width = 128 * (2 if dtype == "float64" else 4)
@@ -266,5 +262,5 @@ def test_hdiff_tiling_covers_every_row_once(monkeypatch, dtype, domain, tail):
     for a, b_, c, d in zip(xt, k, j0, j1):
         rows[a, b_, c:d] += 1
     assert (rows == 1).all()
-    if tail is None:
+    if cfg is None:
         assert (j1 - j0).max() <= 32  # default segments (profiles/hdiff_segments_r01.log)
