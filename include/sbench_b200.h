@@ -226,6 +226,11 @@ int sb200_vadv_components(int dtype, int ncomp,
 /* Multi-GPU halo plumbing for the J-partitioned horizontal diffusion  */
 /* ------------------------------------------------------------------ */
 
+/* Peer memory inside one process that drives several GPUs: after cudaDeviceEnablePeerAccess(peer)
+ * on `device`, kernels (and TMA) running on `device` can address `peer`'s allocations directly.
+ * Already enabled is not an error. */
+int sb200_enable_peer_access(int device, int peer);
+
 /* Peer memory across processes (one process per GPU): cudaIpcGetMemHandle on the BASE of a
  * sb200_malloc allocation (64-byte handle, sent to the neighbour by any host channel),
  * cudaIpcOpenMemHandle / cudaIpcCloseMemHandle on the receiving side.  The mapped pointer
@@ -246,6 +251,29 @@ int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, void* out,
                      int64_t nx, int64_t ny, int64_t nz,
                      int64_t sx, int64_t sy, int64_t sz,
                      int dry_runs, double* time, void* stream);
+
+/* One sweep of a TIME LOOP over J slabs: like sb200_hdiff_peer, plus the ordering a loop needs
+ * when `inp` and `out` swap roles every step (sweep m reads what sweep m-1 wrote, and overwrites
+ * what sweep m-1 read).  The ordering is inside the kernel: the CTAs that sweep the slab's first /
+ * last rows wait (ld.acquire.sys) until the neighbour's sweep m-1 has finished with the rows both
+ * touch, and tell the neighbours when they are done themselves (red.release.sys into the
+ * neighbours' memory over NVLink); every other CTA runs unhindered, the host is not involved.
+ *   arrived        this slab's counters, two zero-initialised uint32 in its own device memory:
+ *                  [0] is pushed by the lower, [1] by the upper neighbour
+ *   notify_lower   address of the LOWER neighbour's arrived[1], mapped into this process
+ *   notify_upper   address of the UPPER neighbour's arrived[0]
+ *   step           m = 0, 1, 2, ...: index of this sweep in the loop; every slab calls with the
+ *                  same sequence.  The fields, their neighbours and the domain must stay the same
+ *                  for the whole loop apart from the inp <-> out swap.
+ * Without neighbours this is sb200_hdiff.  No dry runs (they would advance the counters). */
+int sb200_hdiff_step(int dtype, const void* inp, const void* coeff, void* out,
+                     const void* inp_lower, int64_t ny_lower, int64_t sz_lower,
+                     const void* inp_upper, int64_t ny_upper, int64_t sz_upper,
+                     const uint32_t* arrived, uint32_t* notify_lower, uint32_t* notify_upper,
+                     uint32_t step,
+                     int64_t nx, int64_t ny, int64_t nz,
+                     int64_t sx, int64_t sy, int64_t sz,
+                     double* time, void* stream);
 
 /* Pack `nrows` consecutive j-rows (all nz levels, i range [-hx, nx+hx)) of a
  * field into a contiguous buffer / unpack them again, so that one

@@ -85,6 +85,10 @@ def configurations():
          dict(domain=(2048, 2048, 80), vector_size=8, streaming_stores=True, block_size=(1024, 16, 1), **tuned)),
         ("hdiff_minimummem_2048x2048x80_f64", hdiff.MinimumMem,
          dict(domain=(2048, 2048, 80), vector_size=8, streaming_stores=True, block_size=(1024, 16, 1), **tuned)),
+        ("hdiff_rolling_2048x2048x80_f64", hdiff.Rolling,
+         dict(domain=(2048, 2048, 80), vector_size=8, streaming_stores=True, block_size=(1024, 16, 1), **tuned)),
+        ("hdiff_rolling_128x128x80_f64", hdiff.Rolling,
+         dict(domain=(128, 128, 80), vector_size=4, block_size=(128, 16, 1), **tuned)),
         ("vadv_kinnermost_128x128x80_f64", vadv.KInnermost, dict(domain=(128, 128, 80), **f64)),
         # scripts/sbench_rome_collection.py:244-256
         ("vadv_kmiddlevec_1024x1024x160_f64", vadv.KMiddleVec,
@@ -100,8 +104,11 @@ def configurations():
 
 
 def cuda_configurations():
-    """The reference's own GPU kernels, block sizes from scripts/sbench_h100_collection.py:113-152,
-    rendered for the BASELINE.json sizes and compiled for sm_100 ("the kernel to beat")."""
+    """The reference's own GPU kernels rendered for the BASELINE.json sizes and compiled for sm_100
+    ("the kernel to beat").  Seed: the block sizes of scripts/sbench_h100_collection.py:113-152
+    (names without a size suffix); around it a grid over `block_size` (and `unroll_factor` for the
+    vertical advection) for the variants that lead on Hopper, so that the comparison is against
+    the best B200 configuration of the reference's kernels, not against an H100 tuning."""
     from stencil_benchmarks.benchmarks_collection.stencils.cuda_hip import (
         basic,
         horizontal_diffusion as hdiff,
@@ -113,7 +120,7 @@ def cuda_configurations():
     hd = dict(domain=(2048, 2048, 80), **common)
     va = dict(domain=(1024, 1024, 160), **common)
     ba = dict(domain=(1024, 1024, 80), halo=(1, 1, 1), loop="3D", block_size=(128, 2, 1), **common)
-    return [
+    configs = [
         ("cuda_hdiff_classic", hdiff.Classic, dict(block_size=(32, 12, 1), **hd)),
         ("cuda_hdiff_otf", hdiff.OnTheFly, dict(block_size=(32, 16, 1), loop="3D", **hd)),
         ("cuda_hdiff_otfincache", hdiff.OnTheFlyIncache, dict(block_size=(32, 8, 1), **hd)),
@@ -127,10 +134,39 @@ def cuda_configurations():
         ("cuda_vadv_localmem", vadv.LocalMem, dict(block_size=(128, 1), unroll_factor=28, **va)),
         ("cuda_vadv_sharedmem", vadv.SharedMem, dict(block_size=(64, 1), unroll_factor=0, **va)),
         ("cuda_vadv_localmemmerged", vadv.LocalMemMerged, dict(block_size=(128, 1), unroll_factor=2, **va)),
+        ("cuda_vadv_localmemmerged_uvw", vadv.LocalMemMerged,
+         dict(block_size=(128, 1), unroll_factor=2, all_components=True, **va)),
         ("cuda_basic_copy", basic.Copy, ba),
         ("cuda_basic_avg_i", basic.OnesidedAverage, dict(axis=0, **ba)),
         ("cuda_basic_lap_ij", basic.Laplacian, ba),
     ]
+    # --- B200 sweep ---
+    for by in (4, 8, 16, 32):
+        for bz in (1, 2, 4):
+            if (by, bz) != (8, 2):
+                configs.append((f"cuda_hdiff_jscanshuffle_28x{by}x{bz}", hdiff.JScanShuffle,
+                                dict(block_size=(28, by, bz), **hd)))
+    for bx in (64, 128, 256):
+        for by in (4, 8, 16, 32):
+            if (bx, by) != (128, 4):
+                configs.append((f"cuda_hdiff_jscanotf_{bx}x{by}x1", hdiff.JScanOtf,
+                                dict(block_size=(bx, by, 1), **hd)))
+    for bx, by in ((32, 4), (32, 8), (32, 16), (64, 8), (64, 4)):
+        configs.append((f"cuda_hdiff_classic_{bx}x{by}x1", hdiff.Classic, dict(block_size=(bx, by, 1), **hd)))
+    for by, bz in ((16, 2), (8, 4)):
+        configs.append((f"cuda_hdiff_jscanshuffleincache_28x{by}x{bz}", hdiff.JScanShuffleIncache,
+                        dict(block_size=(28, by, bz), **hd)))
+    for bx in (32, 64, 256):
+        for unroll in (8, 28):
+            configs.append((f"cuda_vadv_localmem_{bx}_u{unroll}", vadv.LocalMem,
+                            dict(block_size=(bx, 1), unroll_factor=unroll, **va)))
+    configs.append(("cuda_vadv_localmem_128_u8", vadv.LocalMem, dict(block_size=(128, 1), unroll_factor=8, **va)))
+    for bx in (32, 64, 256):
+        configs.append((f"cuda_vadv_classic_{bx}_u8", vadv.Classic, dict(block_size=(bx, 1), unroll_factor=8, **va)))
+    for bx in (32, 64):
+        configs.append((f"cuda_vadv_localmemmerged_uvw_{bx}", vadv.LocalMemMerged,
+                        dict(block_size=(bx, 1), unroll_factor=2, all_components=True, **va)))
+    return configs
 
 
 def build_cuda(captured, manifest):

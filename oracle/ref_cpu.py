@@ -57,14 +57,64 @@ def alloc_field(entry):
     return np.ndarray(shape=shape, dtype=dtype, buffer=raw, offset=offset, strides=strides)
 
 
-class Kernel:
-    """One compiled reference kernel: ``kernel(double* time, long long* counter, T* fields...)``."""
+def cpu_model():
+    try:
+        for line in pathlib.Path("/proc/cpuinfo").read_text().splitlines():
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
-    def __init__(self, name, isa=None):
+
+def native_library(name, entry):
+    """The kernel compiled ON THIS MACHINE with the reference's own flags, ``-march=native
+    -mtune=native`` included (openmp/mixin.py:88-101), from the source the reference rendered
+    (oracle/_ref/src, written by build_ref.py).  Cached per CPU model under oracle/_ref/native/.
+    Returns None where that is not possible (no g++, no source): the prebuilt portable-ISA
+    libraries are used then."""
+    import hashlib
+    import shutil
+    import subprocess
+
+    compiler = shutil.which("g++")
+    source = REF / "src" / (name + ".cpp")
+    if compiler is None or not source.exists():
+        return None
+    tag = hashlib.sha1((cpu_model() + "".join(sorted(cpu_flags()))).encode()).hexdigest()[:10]
+    target = REF / "native" / f"{name}.{tag}.so"
+    if not target.exists():
+        target.parent.mkdir(parents=True, exist_ok=True)
+        scratch = target.with_suffix(f".{os.getpid()}.tmp")
+        command = [compiler, "-o", str(scratch), str(source)] + list(entry["compile_flags"]) + [
+            "-march=native", "-mtune=native", "-shared", "-fPIC"]
+        try:
+            result = subprocess.run(command, capture_output=True, text=True, timeout=300)
+        except (OSError, subprocess.SubprocessError):
+            return None
+        if result.returncode != 0:
+            return None
+        os.replace(scratch, target)
+    return target
+
+
+class Kernel:
+    """One compiled reference kernel: ``kernel(double* time, long long* counter, T* fields...)``.
+
+    ``isa``: "native" (default: compiled here with the reference's ``-march=native``, falling back
+    to the best prebuilt level), or one of the prebuilt levels x86-64-v3 / x86-64-v4."""
+
+    def __init__(self, name, isa="native"):
         self.name = name
         self.entry = manifest()[name]
-        self.isa = isa or best_isa()
-        self.library = ctypes.CDLL(str(REF / self.entry["libraries"][self.isa]))
+        path = None
+        if isa in (None, "native"):
+            path = native_library(name, self.entry)
+            isa = "native" if path is not None else best_isa()
+        if path is None:
+            path = REF / self.entry["libraries"][isa]
+        self.isa = isa
+        self.library = ctypes.CDLL(str(path))
         self.function = self.library.kernel
         self.function.restype = ctypes.c_int
 

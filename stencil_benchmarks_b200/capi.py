@@ -74,6 +74,9 @@ PROTOTYPES = {
     "sb200_hdiff_tiling": (_i, [_i, _i64, _i64, _i64, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
                                 ctypes.POINTER(_i64)]),
     "sb200_hdiff_peer": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64] + _geom + [_i, _dp, _vp]),
+    "sb200_hdiff_step": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, ctypes.c_uint32]
+                         + _geom + [_dp, _vp]),
+    "sb200_enable_peer_access": (_i, [_i, _i]),
     "sb200_ipc_get_handle": (_i, [_vp, _vp]),
     "sb200_ipc_open_handle": (_i, [_vp, ctypes.POINTER(_vp)]),
     "sb200_ipc_close_handle": (_i, [_vp]),

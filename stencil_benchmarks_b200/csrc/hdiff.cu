@@ -224,6 +224,31 @@ struct PeerMaps {
   int has_lower, has_upper;
 };
 
+// Time loop over J slabs (inp and out swap roles every step): what orders the sweeps of
+// neighbouring GPUs.  The CTAs of a slab's first / last segment ("edge CTAs") are the only ones
+// that read a neighbour's rows and the only ones whose output rows a neighbour reads.  When an edge
+// CTA has stored its rows, each of its four consumer warps adds 1 to a counter in the neighbour's
+// memory (red.release.sys over NVLink) -- after sweep m-1 the counter stands at m * (edge warps per
+// sweep).  The producer of an edge CTA of sweep m spins on the LOCAL counter its neighbour pushes
+// (ld.acquire.sys) until it has reached that value before it issues its first load: then the
+// neighbour's rows of the field it is about to read are complete (they were written in the
+// neighbour's sweep m-1), and the neighbour no longer reads the rows this CTA is about to overwrite
+// (it read them in its sweep m-1).  No host involvement, no extra launch; CTAs that are not on an
+// edge never look at a flag.  Sweeps of one GPU are ordered by the stream, so a waiting CTA only
+// ever depends on sweeps that do not depend on it.
+struct StepFlags {
+  const unsigned int* arrived[2];  // local counters: [0] pushed by the lower, [1] by the upper neighbour
+  unsigned int* notify[2];         // the neighbours' counters this slab pushes: [0] lower, [1] upper
+  unsigned int wait_value;         // m * edge warps per sweep; 0: nothing to wait for
+};
+
+__device__ __forceinline__ void wait_for_neighbour(const unsigned int* counter, unsigned int value) {
+  unsigned int seen;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+  } while (int(seen - value) < 0);
+}
+
 // Work decomposition of one sweep: CTA = (256-wide i tile, segment of jt rows, level k), numbered
 // i tile fastest, then segment, then level: the CTAs resident at any time sweep one compact band of
 // the field, and the eight i tiles of a segment, which together read whole rows, run side by side.
@@ -242,8 +267,9 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
     hdiff_tma_kernel(const __grid_constant__ CUtensorMap map_inp,
                      const __grid_constant__ CUtensorMap map_halo,
                      const __grid_constant__ CUtensorMap map_coeff,
-                     const __grid_constant__ PeerMaps peer, T* __restrict__ out, int nx,
-                     int ny, const HdiffTiling tiling, int64_t sy, int64_t sz) {
+                     const __grid_constant__ PeerMaps peer, const StepFlags flags,
+                     T* __restrict__ out, int nx, int ny, const HdiffTiling tiling, int64_t sy,
+                     int64_t sz) {
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
   constexpr int STAGE = tmacfg::stage_bytes(R);
@@ -284,6 +310,13 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
         }
       }
       const int c0 = it / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
+      if (PEER && flags.wait_value != 0) {
+        // time loop: an edge CTA starts once the neighbour's previous sweep has finished with the
+        // rows both touch; the async proxy (TMA) must not run ahead of the acquire
+        if (peer.has_lower && jb == 0) wait_for_neighbour(flags.arrived[0], flags.wait_value);
+        if (peer.has_upper && je == ny) wait_for_neighbour(flags.arrived[1], flags.wait_value);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
       for (int n = 0; n < nstages; ++n) {
         const int slot = n % S;
         if (n >= S) tma::mbar_wait(&empty[slot], ((n / S) - 1) & 1);
@@ -399,6 +432,20 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) tma::mbar_arrive(&empty[slot]);
+  }
+  if (PEER) {
+    // time loop: tell the neighbours that this edge CTA's rows are written (and that it no longer
+    // reads theirs); the release at system scope covers the whole warp's stores
+    const bool lower_edge = peer.has_lower && jb == 0 && flags.notify[0] != nullptr;
+    const bool upper_edge = peer.has_upper && je == ny && flags.notify[1] != nullptr;
+    if (lower_edge || upper_edge) {
+      __threadfence_system();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {
+        if (lower_edge) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flags.notify[0]) : "memory");
+        if (upper_edge) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flags.notify[1]) : "memory");
+      }
+    }
   }
 }
 
@@ -541,7 +588,7 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
                      int64_t sy, int64_t sz, int jt_request, int dry_runs, double* time,
                      cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
                      int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
-                     int64_t sz_upper = 0) {
+                     int64_t sz_upper = 0, const StepFlags* step_flags = nullptr, unsigned step = 0) {
   constexpr int VEC = VecN<T>::value;
   constexpr int TW = tmacfg::kConsumers * VEC;
   *used = false;
@@ -563,13 +610,19 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
       ensure_dynamic_smem(hdiff_tma_kernel<T, R, S, true>, smem, attr_peer))
     return 1;
   *used = true;
+  StepFlags flags{{nullptr, nullptr}, {nullptr, nullptr}, 0};
+  if (step_flags != nullptr) {
+    flags = *step_flags;
+    // every edge CTA notifies once per consumer warp: xtiles * levels CTAs per edge and sweep
+    flags.wait_value = step * unsigned(xtiles * nz) * unsigned(tmacfg::kConsumers / 32);
+  }
   auto launch = [&] {
     if (with_peers)
       hdiff_tma_kernel<T, R, S, true><<<grid, tmacfg::kThreads, smem, stream>>>(
-          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz);
+          maps.inp, maps.halo, maps.coeff, maps.peer, flags, out, int(nx), int(ny), tiling, sy, sz);
     else
       hdiff_tma_kernel<T, R, S, false><<<grid, tmacfg::kThreads, smem, stream>>>(
-          maps.inp, maps.halo, maps.coeff, maps.peer, out, int(nx), int(ny), tiling, sy, sz);
+          maps.inp, maps.halo, maps.coeff, maps.peer, flags, out, int(nx), int(ny), tiling, sy, sz);
     count_launch();
   };
   return timed(launch, dry_runs, time, stream);
@@ -581,10 +634,10 @@ int launch_hdiff_tma(const T* inp, const T* coeff, T* out, int64_t nx, int64_t n
                      int64_t sz, int jt_request, int dry_runs, double* time,
                      cudaStream_t stream, bool* used, const T* inp_lower = nullptr, int64_t ny_lower = 0,
                      int64_t sz_lower = 0, const T* inp_upper = nullptr, int64_t ny_upper = 0,
-                     int64_t sz_upper = 0) {
+                     int64_t sz_upper = 0, const StepFlags* step_flags = nullptr, unsigned step = 0) {
 #define SB200_TMA_ARGS                                                                              \
   inp, coeff, out, nx, ny, nz, sy, sz, jt_request, dry_runs, time, stream, used, inp_lower, \
-      ny_lower, sz_lower, inp_upper, ny_upper, sz_upper
+      ny_lower, sz_lower, inp_upper, ny_upper, sz_upper, step_flags, step
   // 4 rows x 4 stages is the best of the shapes measured (4x3, 8x2, 8x3, 2x6 are within 2.5 %:
   // profiles/hdiff_variants_r01.log); 4x3 is kept as the alternative for tuning runs
   if (hdiff_config().pipeline == 1) return launch_hdiff_tma_rs<T, 4, 3>(SB200_TMA_ARGS);
@@ -639,15 +692,21 @@ int launch_hdiff(const T* inp, const T* coeff, T* out, int64_t nx, int64_t ny, i
 
 using namespace sb200;
 
-extern "C" int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, void* out,
-                                const void* inp_lower, int64_t ny_lower, int64_t sz_lower,
-                                const void* inp_upper, int64_t ny_upper, int64_t sz_upper, int64_t nx,
-                                int64_t ny, int64_t nz, int64_t sx, int64_t sy, int64_t sz, int dry_runs,
-                                double* time, void* stream) {
-  if (nx <= 0 || ny <= 0 || nz <= 0) return fail("sb200_hdiff_peer: domain must be positive");
-  if (sx != 1) return fail("sb200_hdiff_peer: only layout (2,1,0) is supported (unit stride along i)");
+namespace {
+int hdiff_peer_entry(const char* who, int dtype, const void* inp, const void* coeff, void* out,
+                     const void* inp_lower, int64_t ny_lower, int64_t sz_lower, const void* inp_upper,
+                     int64_t ny_upper, int64_t sz_upper, const StepFlags* flags, unsigned step, int64_t nx,
+                     int64_t ny, int64_t nz, int64_t sx, int64_t sy, int64_t sz, int dry_runs, double* time,
+                     void* stream) {
+  auto failed = [who](const char* what) {
+    std::fprintf(stderr, "%s: %s\n", who, what);
+    std::fflush(stderr);
+    return 1;
+  };
+  if (nx <= 0 || ny <= 0 || nz <= 0) return failed("domain must be positive");
+  if (sx != 1) return failed("only layout (2,1,0) is supported (unit stride along i)");
   if ((inp_lower != nullptr && ny_lower < 2) || (inp_upper != nullptr && ny_upper < 2))
-    return fail("sb200_hdiff_peer: neighbouring slabs must hold at least two rows");
+    return failed("neighbouring slabs must hold at least two rows");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const HdiffConfig cfg = hdiff_config();
   bool used = false;
@@ -655,26 +714,57 @@ extern "C" int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, v
   const bool aligned = aligned_to(inp, 16) && aligned_to(coeff, 16) && aligned_to(out, 16) &&
                        (inp_lower == nullptr || aligned_to(inp_lower, 16)) &&
                        (inp_upper == nullptr || aligned_to(inp_upper, 16));
-  if (!aligned) return fail("sb200_hdiff_peer: fields must be 16-byte aligned");
+  if (!aligned) return failed("fields must be 16-byte aligned");
   if (dtype == SB200_F64) {
-    if (sy % 2 || sz % 2 || sz_lower % 2 || sz_upper % 2)
-      return fail("sb200_hdiff_peer: strides must keep rows 16-byte aligned");
+    if (sy % 2 || sz % 2 || sz_lower % 2 || sz_upper % 2) return failed("strides must keep rows 16-byte aligned");
     rc = launch_hdiff_tma<double>(static_cast<const double*>(inp), static_cast<const double*>(coeff),
                                   static_cast<double*>(out), nx, ny, nz, sy, sz, cfg.jt, dry_runs, time, s,
                                   &used, static_cast<const double*>(inp_lower), ny_lower, sz_lower,
-                                  static_cast<const double*>(inp_upper), ny_upper, sz_upper);
+                                  static_cast<const double*>(inp_upper), ny_upper, sz_upper, flags, step);
   } else if (dtype == SB200_F32) {
-    if (sy % 4 || sz % 4 || sz_lower % 4 || sz_upper % 4)
-      return fail("sb200_hdiff_peer: strides must keep rows 16-byte aligned");
+    if (sy % 4 || sz % 4 || sz_lower % 4 || sz_upper % 4) return failed("strides must keep rows 16-byte aligned");
     rc = launch_hdiff_tma<float>(static_cast<const float*>(inp), static_cast<const float*>(coeff),
                                  static_cast<float*>(out), nx, ny, nz, sy, sz, cfg.jt, dry_runs, time, s,
                                  &used, static_cast<const float*>(inp_lower), ny_lower, sz_lower,
-                                 static_cast<const float*>(inp_upper), ny_upper, sz_upper);
+                                 static_cast<const float*>(inp_upper), ny_upper, sz_upper, flags, step);
   } else {
-    return fail("sb200_hdiff_peer: unsupported dtype");
+    return failed("unsupported dtype");
   }
-  if (rc == 0 && !used) return fail("sb200_hdiff_peer: the TMA path is not available for these fields");
+  if (rc == 0 && !used) return failed("the TMA path is not available for these fields");
   return rc;
+}
+}  // namespace
+
+extern "C" int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, void* out,
+                                const void* inp_lower, int64_t ny_lower, int64_t sz_lower,
+                                const void* inp_upper, int64_t ny_upper, int64_t sz_upper, int64_t nx,
+                                int64_t ny, int64_t nz, int64_t sx, int64_t sy, int64_t sz, int dry_runs,
+                                double* time, void* stream) {
+  return hdiff_peer_entry("sb200_hdiff_peer", dtype, inp, coeff, out, inp_lower, ny_lower, sz_lower, inp_upper,
+                          ny_upper, sz_upper, nullptr, 0, nx, ny, nz, sx, sy, sz, dry_runs, time, stream);
+}
+
+extern "C" int sb200_hdiff_step(int dtype, const void* inp, const void* coeff, void* out,
+                                const void* inp_lower, int64_t ny_lower, int64_t sz_lower,
+                                const void* inp_upper, int64_t ny_upper, int64_t sz_upper,
+                                const uint32_t* arrived, uint32_t* notify_lower, uint32_t* notify_upper,
+                                uint32_t step, int64_t nx, int64_t ny, int64_t nz, int64_t sx, int64_t sy,
+                                int64_t sz, double* time, void* stream) {
+  if (inp_lower == nullptr && inp_upper == nullptr) {
+    // a slab without neighbours: nothing to order, the plain sweep
+    return sb200_hdiff(dtype, inp, coeff, out, nx, ny, nz, sx, sy, sz, 0, time, stream);
+  }
+  if (arrived == nullptr || (inp_lower != nullptr && notify_lower == nullptr) ||
+      (inp_upper != nullptr && notify_upper == nullptr))
+    return fail("sb200_hdiff_step: a slab with neighbours needs its own counters and theirs");
+  StepFlags flags;
+  flags.arrived[0] = arrived;
+  flags.arrived[1] = arrived + 1;
+  flags.notify[0] = inp_lower != nullptr ? notify_lower : nullptr;
+  flags.notify[1] = inp_upper != nullptr ? notify_upper : nullptr;
+  flags.wait_value = 0;
+  return hdiff_peer_entry("sb200_hdiff_step", dtype, inp, coeff, out, inp_lower, ny_lower, sz_lower, inp_upper,
+                          ny_upper, sz_upper, &flags, step, nx, ny, nz, sx, sy, sz, 0, time, stream);
 }
 
 extern "C" int sb200_hdiff_tiling(int dtype, int64_t nx, int64_t ny, int64_t nz, int* xtiles, int* segments,

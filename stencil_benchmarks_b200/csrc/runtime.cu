@@ -105,7 +105,8 @@ int sb200_free(void* dptr) {
 
 int sb200_host_alloc(void** hptr, size_t nbytes) {
   if (hptr == nullptr) return fail("sb200_host_alloc: hptr is NULL");
-  SB200_CHECK(cudaHostAlloc(hptr, nbytes, cudaHostAllocDefault));
+  // portable: one process may drive several devices (the partitioned benchmarks)
+  SB200_CHECK(cudaHostAlloc(hptr, nbytes, cudaHostAllocPortable));
   return 0;
 }
 
@@ -208,6 +209,23 @@ int sb200_event_elapsed(void* start, void* stop, double* seconds) {
   SB200_CHECK(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
   SB200_CHECK(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
   *seconds = double(ms) / 1000.0;
+  return 0;
+}
+
+int sb200_enable_peer_access(int device, int peer) {
+  int previous = 0, possible = 0;
+  SB200_CHECK(cudaGetDevice(&previous));
+  SB200_CHECK(cudaDeviceCanAccessPeer(&possible, device, peer));
+  if (!possible) return fail("sb200_enable_peer_access: the devices cannot access each other's memory");
+  SB200_CHECK(cudaSetDevice(device));
+  const cudaError_t status = cudaDeviceEnablePeerAccess(peer, 0);
+  if (status != cudaSuccess && status != cudaErrorPeerAccessAlreadyEnabled) {
+    cudaSetDevice(previous);
+    return report_cuda_error(status, "cudaDeviceEnablePeerAccess");
+  }
+  while (cudaGetLastError() != cudaSuccess) {
+  }
+  SB200_CHECK(cudaSetDevice(previous));
   return 0;
 }
 

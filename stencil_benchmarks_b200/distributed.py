@@ -234,3 +234,95 @@ class PeerSlabs:
         for mapped in self._opened:
             self._lib.sb200_ipc_close_handle(mapped)
         self._opened = []
+
+
+class TimeLoop:
+    """A time loop of horizontal diffusion on one J slab: sweep m reads field X_m and writes
+    X_(m+1), with X_0 = the instance's ``inp`` mirror, X_1 = its ``out`` mirror, X_2 = X_0 again...
+    (``coeff`` stays).  Halo values never change: both buffers start as copies of ``inp``, sweeps
+    write interior points only, so the global boundary acts as a fixed-value condition -- exactly
+    what applying the oracle again and again to ``out[interior]`` computes.
+
+    With neighbours (``world_size`` > 1) the sweeps are ``sb200_hdiff_step`` launches: halo rows are
+    read from the neighbours' buffers over NVLink and the sweeps of neighbouring GPUs order
+    themselves through counters in peer memory (include/sbench_b200.h).  Nothing but kernel
+    launches happens per step: no host synchronisation, no barrier, no copy.
+
+    New with respect to the reference, which sweeps once per ``run()`` on one GPU.
+    """
+
+    #: own allocation for the two counters: large enough that the CUDA allocator does not carve it
+    #: out of a block shared with other buffers (an IPC handle always maps a whole block)
+    FLAG_BYTES = 2 << 20
+
+    def __init__(self, bench, mirrors, dist=None, rank=0, world_size=1, group=None):
+        import ctypes
+
+        from . import capi
+        from .tools import fields
+
+        self._ctypes = ctypes
+        self._lib = capi.library()
+        self._capi = capi
+        self.bench = bench
+        self.code = capi.dtype_code(bench.dtype)
+        self.geometry = bench.geometry()
+        data = bench.data(0)
+        self._nbytes = fields.nbytes(data.inp)
+        self.first = [mirrors["inp"][1], mirrors["out"][1]]
+        interior = sum(int(s) * int(h) for s, h in zip(data.inp.strides, bench.halo))
+        self.interior = [first + interior for first in self.first]
+        self.coeff = bench.interior_ptr(mirrors["coeff"][1], data.coeff).value
+        self._lib.sb200_memcpy_d2d(ctypes.c_void_p(self.first[1]), ctypes.c_void_p(self.first[0]),
+                                   self._nbytes, None, 1)
+        self.count = 0
+        self.flags = capi.DeviceBuffer(self.FLAG_BYTES)
+        self._lib.sb200_memset(ctypes.c_void_p(self.flags.ptr), 0, self.FLAG_BYTES, None, 1)
+        self.peers = [None, None]
+        self.peer_flags = None
+        self._dist, self._group = dist, group
+        if world_size > 1:
+            ny, sz = int(bench.domain[1]), int(bench.strides[2])
+            bases = [mirrors["inp"][0].ptr, mirrors["out"][0].ptr]
+            self.peers = [PeerSlabs(dist, rank, world_size, bases[n], self.interior[n], ny, sz, group=group)
+                          for n in range(2)]
+            self.peer_flags = PeerSlabs(dist, rank, world_size, self.flags.ptr, self.flags.ptr, 0, 0, group=group)
+            dist.barrier(group=group)  # every rank's buffers and counters are in place
+
+    def step(self, stream=None):
+        """Enqueue sweep number ``count`` on ``stream``."""
+        c = self._ctypes
+        vp = c.c_void_p
+        m = self.count
+        src, dst = m % 2, (m + 1) % 2
+        peers = self.peers[src]
+        if peers is None:
+            status = self._lib.raw.sb200_hdiff(self.code, vp(self.interior[src]), vp(self.coeff),
+                                               vp(self.interior[dst]), *self.geometry, 0, None, vp(stream))
+        else:
+            flags = self.peer_flags
+            status = self._lib.raw.sb200_hdiff_step(
+                self.code, vp(self.interior[src]), vp(self.coeff), vp(self.interior[dst]),
+                vp(peers.lower), peers.ny_lower, peers.sz_lower, vp(peers.upper), peers.ny_upper, peers.sz_upper,
+                vp(self.flags.ptr),
+                vp(flags.lower + 4 if flags.lower is not None else None),   # lower neighbour's arrived[1]
+                vp(flags.upper if flags.upper is not None else None),       # upper neighbour's arrived[0]
+                m, *self.geometry, None, vp(stream))
+        if status != 0:
+            raise RuntimeError(f"sweep {m} of the time loop failed (status {status}); see stderr")
+        self.count += 1
+
+    def download(self, host):
+        """The current state X_count (whole padded field) into the host array ``host``."""
+        self._capi.memcpy_d2h(host.ctypes.data, self.first[self.count % 2], self._nbytes)
+        return host
+
+    def close(self):
+        if self._dist is not None and self.peer_flags is not None:
+            self._capi.synchronize()
+            self._dist.barrier(group=self._group)
+        for peers in self.peers + [self.peer_flags]:
+            if peers is not None:
+                peers.close()
+        self.peers = [None, None]
+        self.peer_flags = None

@@ -157,6 +157,12 @@ def test_reference_cli_runs_the_backend(tmp_path):
                  "laplacian", "--domain", "10", "10", "10", "--along-z")
     assert result.returncode == 0, result.stdout + result.stderr
 
+    out = tmp_path / "partitioned.csv"
+    result = run(CLI, tmp_path, "--executions", "2", "--output", str(out), "stencils", "b200",
+                 "horizontal-diffusion", "partitioned", "--domain", "300", "64", "5", "--gpus", "1")
+    assert result.returncode == 0, result.stdout + result.stderr
+    assert list(pd.read_csv(out)["gpus"]) == [1, 1]
+
     out = tmp_path / "stream.csv"
     result = run(CLI, tmp_path, "--executions", "2", "--output", str(out), "stream", "b200", "native",
                  "--array-size", "4194304")
@@ -192,3 +198,26 @@ def test_collection_script_writes_the_reference_csv(tmp_path):
     assert len(table) == 3 * 7  # 3 executions x domains 32^2 ... 2048^2 (x 80)
     assert (table["bandwidth"] > 0).all() and set(table["dtype"]) == {"float32"}
     assert set(table["name"]) == {"fused"}
+
+
+def test_partitioned_class_is_verified_by_the_reference_oracle(tmp_path):
+    """All GPUs of the box (at least 2): the gathered global field passes the reference's
+    verify_stencil."""
+    import sys as _sys
+    _sys.path.insert(0, str(ROOT))
+    from stencil_benchmarks_b200 import capi
+
+    gpus = min(capi.device_count(), 8)
+    if gpus < 2:
+        pytest.skip("needs two GPUs")
+    code = """
+import sys
+from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+for dtype in ("float64", "float32"):
+    bench = horizontal_diffusion.Partitioned(domain=(520, 264, 6), dtype=dtype, gpus=int(sys.argv[1]), verify=True)
+    print(dtype, bench.run()["bandwidth"])
+print("verified")
+"""
+    result = run(code, tmp_path, str(gpus))
+    assert result.returncode == 0, result.stdout + result.stderr
+    assert "verified" in result.stdout

@@ -241,3 +241,155 @@ def test_partitioned_basic_matches_global_oracle(case):
     results = mp.Manager().dict()
     mp.spawn(_basic_worker, args=(2, _free_port(), case, results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def _time_loop_worker(rank, world, port, domain, steps, results):
+    """K sweeps of the time loop (inp/out swapped every step, neighbours ordered by the in-kernel
+    step flags) against the oracle applied K times to the global field."""
+    import torch
+    import torch.distributed as dist
+
+    from oracle import native
+    from stencil_benchmarks_b200 import distributed
+    from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nx, ny_global, nz = domain
+        halo = (3, 3, 3)
+        rng = np.random.default_rng(33)
+        shape = tuple(d + 2 * h for d, h in zip(domain, halo))
+        g_inp, g_coeff = np.asfortranarray(rng.random(shape)), np.asfortranarray(rng.random(shape))
+        start, ny = distributed.split_rows(ny_global, world)[rank]
+        bench = horizontal_diffusion.Fused(domain=(nx, ny, nz), halo=halo, verify=False, device=rank)
+        data = bench.data()
+        rows = slice(start, start + ny + 6)
+        data.inp[...] = g_inp[:, rows, :]
+        data.coeff[...] = g_coeff[:, rows, :]
+        lower, upper = distributed.neighbours(rank, world)
+        if lower is not None:
+            data.inp[:, :3, :] = np.nan  # never read: the neighbour's rows come over NVLink
+        if upper is not None:
+            data.inp[:, 3 + ny:, :] = np.nan
+        mirrors = bench._device_fields(data)
+        bench.upload(data, mirrors)
+        loop = distributed.TimeLoop(bench, mirrors, dist, rank, world)
+        stream = torch.cuda.current_stream().cuda_stream
+        # no host synchronisation between the sweeps: rank 1 even starts late
+        if rank == 1:
+            import time
+            time.sleep(0.05)
+        for _ in range(steps):
+            loop.step(stream)
+        torch.cuda.synchronize()
+        state = loop.download(bench.empty_field())
+        loop.close()
+        x, y = g_inp.copy(order="F"), g_inp.copy(order="F")
+        for _ in range(steps):
+            native.hdiff(x, g_coeff, y, halo)
+            x, y = y, x
+        ok = np.allclose(state[3:-3, 3:3 + ny, 3:-3], x[3:-3, 3 + start:3 + start + ny, 3:-3],
+                         rtol=1e-12, atol=1e-14)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("domain,steps", [((300, 64, 5), 7), ((512, 259, 3), 12), ((1100, 40, 9), 25)])
+def test_time_loop_orders_neighbouring_gpus(domain, steps):
+    import torch.multiprocessing as mp
+
+    world = min(capi.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs two GPUs")
+    if domain[1] // world < 8:
+        world = 2
+    results = mp.Manager().dict()
+    mp.spawn(_time_loop_worker, args=(world, _free_port(), domain, steps, results), nprocs=world, join=True)
+    assert dict(results) == {rank: True for rank in range(world)}
+
+
+def _partitioned_run_worker(rank, world, port, domain, chunks, results):
+    """run() of an instance that sweeps one J slab (attach_neighbours): uploads, ordering against
+    the neighbours, fused halo reads and downloads through the plugin call itself."""
+    import torch
+    import torch.distributed as dist
+
+    from stencil_benchmarks_b200 import distributed
+    from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nx, ny_global, nz = domain
+        halo = (3, 3, 3)
+        rng = np.random.default_rng(8)
+        shape = tuple(d + 2 * h for d, h in zip(domain, halo))
+        g_inp, g_coeff = rng.random(shape), rng.random(shape)
+        start, ny = distributed.split_rows(ny_global, world)[rank]
+        bench = horizontal_diffusion.Fused(domain=(nx, ny, nz), halo=halo, verify=False, device=rank,
+                                           chunks=chunks)
+        data = bench.data()
+        rows = slice(start, start + ny + 6)
+        data.inp[...] = g_inp[:, rows, :]
+        data.coeff[...] = g_coeff[:, rows, :]
+        lower, upper = distributed.neighbours(rank, world)
+        if lower is not None:
+            data.inp[:, :3, :] = np.nan
+        if upper is not None:
+            data.inp[:, 3 + ny:, :] = np.nan
+        peers = distributed.attach_neighbours(bench, dist, rank, world)
+        for _ in range(2):  # the second run re-uploads while the neighbours may still be sweeping
+            data.out[...] = 0.0
+            result = bench.run()
+        assert result["time"] > 0
+        peers.close()
+        expected = stencils.hdiff(g_inp, g_coeff)
+        ok = np.allclose(data.out[3:-3, 3:3 + ny, 3:-3], expected[3:-3, 3 + start:3 + start + ny, 3:-3],
+                         rtol=1e-13, atol=1e-14)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_partitioned_run_through_the_plugin(chunks):
+    import torch.multiprocessing as mp
+
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    results = mp.Manager().dict()
+    mp.spawn(_partitioned_run_worker, args=(2, _free_port(), (520, 96, 4), chunks, results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+@pytest.mark.parametrize("dtype,domain,gpus", [("float64", (300, 64, 5), 2), ("float32", (1030, 131, 3), 2),
+                                               ("float64", (520, 259, 4), 0)])
+def test_partitioned_plugin_class(dtype, domain, gpus):
+    """`stencils b200 horizontal-diffusion partitioned`: one process drives the GPUs, halo rows come
+    from the neighbouring device's slab (peer access), the gathered field matches the oracle."""
+    from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+
+    available = capi.device_count()
+    if available < 2:
+        pytest.skip("needs two GPUs")
+    gpus = gpus or min(available, 8)  # 0: every GPU of the box
+    bench = horizontal_diffusion.Partitioned(domain=domain, dtype=dtype, gpus=gpus, verify=False, seed=11,
+                                             dry_runs=1)
+    data = bench.data()
+    before = [np.array(f, copy=True) for f in data]
+    result = bench.run()
+    assert result["gpus"] == gpus and result["time"] > 0
+    expected = stencils.hdiff(before[0], before[1], halo=bench.halo)
+    inner = bench.inner_slice()
+    np.testing.assert_allclose(data.out[inner], expected[inner], **stencils.tolerances(dtype))
+    assert np.array_equal(data.inp, before[0]) and np.array_equal(data.coeff, before[1])
+    # halo of out untouched (only interior rows are gathered)
+    mask = np.ones(data.out.shape, dtype=bool)
+    mask[inner] = False
+    assert np.array_equal(data.out[mask], before[2][mask])

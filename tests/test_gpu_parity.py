@@ -17,6 +17,7 @@ import numpy as np
 import pytest
 
 from oracle import native, stencils
+from stencil_benchmarks_b200 import capi
 from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import (
     basic,
     horizontal_diffusion,
@@ -401,3 +402,46 @@ def test_vadv_float32_wide_batches(all_components):
         # the columns next to a batch border (i = 255, 256, 511, 512) must be as good as the rest
         for i in (255, 256, 511, 512):
             assert bad[i].mean() < 5e-2, f"{c}: column block i={i} differs"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,domain,steps", [("float64", (300, 70, 5), 9), ("float32", (520, 33, 3), 4)])
+def test_time_loop_single_gpu(dtype, domain, steps):
+    """TimeLoop without neighbours: inp/out swapped every sweep, halos fixed -- the oracle applied
+    `steps` times."""
+    from oracle import native
+    from stencil_benchmarks_b200 import distributed
+
+    bench = horizontal_diffusion.Fused(domain=domain, dtype=dtype, verify=False, seed=3)
+    data = bench.data()
+    mirrors = bench._device_fields(data)
+    bench.upload(data, mirrors)
+    loop = distributed.TimeLoop(bench, mirrors)
+    for _ in range(steps):
+        loop.step()
+    capi.synchronize()
+    state = loop.download(bench.empty_field())
+    x, y = bench.empty_field(), bench.empty_field()
+    x[...] = data.inp
+    y[...] = data.inp
+    for _ in range(steps):
+        native.hdiff(x, data.coeff, y, tuple(bench.halo))
+        x, y = y, x
+    inner = bench.inner_slice()
+    tol = dict(rtol=1e-12, atol=1e-14) if dtype == "float64" else dict(rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(state[inner], x[inner], **tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_partitioned_class_on_one_gpu(dtype):
+    """The multi-GPU benchmark class degenerates to one slab: scatter, sweep, gather."""
+    bench = horizontal_diffusion.Partitioned(domain=(300, 41, 6), dtype=dtype, gpus=1, verify=False, seed=5)
+    data = bench.data()
+    before = [np.array(f, copy=True) for f in data]
+    result = bench.run()
+    assert result["gpus"] == 1 and result["time"] > 0 and result["bandwidth"] > 0
+    expected = stencils.hdiff(before[0], before[1], halo=bench.halo)
+    inner = bench.inner_slice()
+    assert close(data.out[inner], expected[inner], dtype)
+    assert np.array_equal(data.inp, before[0]) and np.array_equal(data.coeff, before[1])

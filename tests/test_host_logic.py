@@ -37,6 +37,7 @@ def test_registered_command_names():
         "stencils b200 basic empty", "stencils b200 basic copy",
         "stencils b200 basic onesided-average", "stencils b200 basic symmetric-average",
         "stencils b200 basic laplacian", "stencils b200 horizontal-diffusion fused",
+        "stencils b200 horizontal-diffusion partitioned",
         "stencils b200 vertical-advection thomas", "stream b200 native",
     }
 

@@ -17,7 +17,8 @@ def inner(entry):
     return tuple(slice(h, h + d) for d, h in zip(entry["domain"], entry["halo"]))
 
 
-@pytest.mark.parametrize("name", ["hdiff_otf_128x128x80_f64", "hdiff_otfvec_128x128x80_f64"])
+@pytest.mark.parametrize("name", ["hdiff_otf_128x128x80_f64", "hdiff_otfvec_128x128x80_f64",
+                                  "hdiff_rolling_128x128x80_f64"])
 def test_reference_openmp_hdiff_matches_oracle(name):
     kernel = ref_cpu.Kernel(name)
     inp, coeff, out = kernel.fields(seed=4)
