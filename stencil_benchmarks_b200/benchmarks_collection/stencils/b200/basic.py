@@ -24,7 +24,7 @@ class BasicStencilMixin(StencilMixin):
 
     def launch(self, pointers, dry_runs, time_ptr, stream, domain=None, rows=None):
         axis, mask = self.axis_and_mask()
-        self._lib.sb200_basic(
+        self._kernels.sb200_basic(
             self.kind, self._dtype_code, pointers["inp"], pointers["out"], *self.geometry(domain),
             axis, mask, dry_runs, time_ptr, _vp(stream),
         )

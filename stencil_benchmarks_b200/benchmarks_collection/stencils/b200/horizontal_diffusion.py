@@ -35,7 +35,7 @@ class HorizontalDiffusionMixin(StencilMixin):
     def launch(self, pointers, dry_runs, time_ptr, stream, domain=None, rows=None):
         peers = self.peers
         if peers is None:
-            self._lib.sb200_hdiff(
+            self._kernels.sb200_hdiff(
                 self._dtype_code, pointers["inp"], pointers["coeff"], pointers["out"],
                 *self.geometry(domain), dry_runs, time_ptr, _vp(stream),
             )
@@ -45,7 +45,7 @@ class HorizontalDiffusionMixin(StencilMixin):
         j0, j1 = rows if rows is not None else (0, int(self.domain[1]))
         lower = peers.lower if j0 == 0 else None
         upper = peers.upper if j1 == int(self.domain[1]) else None
-        self._lib.sb200_hdiff_peer(
+        self._kernels.sb200_hdiff_peer(
             self._dtype_code, pointers["inp"], pointers["coeff"], pointers["out"],
             _vp(lower), peers.ny_lower, peers.sz_lower, _vp(upper), peers.ny_upper, peers.sz_upper,
             *self.geometry(domain), dry_runs, time_ptr, _vp(stream),
@@ -191,6 +191,7 @@ class Partitioned(HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
 
     def _run_partitioned(self, data):
         lib = self._lib
+        kernels = self._kernels
         slabs = self._partition(data)
         nx, _, nz = (int(d) for d in self.domain)
         hy, hk = int(self.halo[1]), int(self.halo[2])
@@ -209,7 +210,7 @@ class Partitioned(HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
         def sweep(slab, index, dry_runs):
             lower = slabs[index - 1] if index > 0 else None
             upper = slabs[index + 1] if index < last else None
-            lib.sb200_hdiff_peer(
+            kernels.sb200_hdiff_peer(
                 self._dtype_code, _vp(slab["interior"]["inp"]), _vp(slab["interior"]["coeff"]),
                 _vp(slab["interior"]["out"]),
                 _vp(lower["interior"]["inp"] if lower else None), lower["ny"] if lower else 0,

@@ -6,9 +6,11 @@ Counterpart of the reference's ``cuda_hip.StencilMixin``
 =====================  =====================================================
 reference               here
 =====================  =====================================================
-render Jinja + nvcc     pre-built ``libsbench_b200.so`` (sm_100a only); a
-at ``setup()``          missing library is a ``ParameterError`` like a failed
-(mixin.py:60-84)        compilation is there
+render Jinja + nvcc     pre-built ``libsbench_b200.so`` (sm_100a only), or --
+at ``setup()``          with ``compiler`` given -- the same sources compiled at
+(mixin.py:60-84)        ``setup()`` through ``tools.compilation.GnuLibrary``; a
+                        missing library / failed compilation is a
+                        ``ParameterError`` as it is there
 ``on_device``           ``_device_fields``: device mirrors with the host's
 (mixin.py:125-160):     strides, allocated once per data set; per run H2D of
 cudaMalloc + H2D of     the fields the stencil READS and D2H of the fields it
@@ -36,6 +38,10 @@ _vp = ctypes.c_void_p
 
 class StencilMixin(Benchmark):
     # names kept from the reference mixin (mixin.py:51-58) where they still mean something
+    compiler = Parameter(
+        "compiler path: if given, the kernels are compiled at setup() through the reference's "
+        "tools.compilation path (as its cuda_hip backend does); empty: the prebuilt library", "")
+    compiler_flags = Parameter("additional compiler flags (with `compiler`)", "")
     backend = Parameter("GPU programming model (CUDA only)", "cuda", choices=["cuda"])
     gpu_architecture = Parameter("GPU architecture (Blackwell B200 only)", "sm_100a",
                                  choices=["sm_100a"])
@@ -77,6 +83,9 @@ class StencilMixin(Benchmark):
             raise ParameterError(str(error)) from error
         try:
             self._lib = capi.library()
+            # the C entry point of the stencil itself: from the prebuilt library, or compiled now
+            self._kernels = (capi.jit_library(self.compiler, self.compiler_flags, self.kernel_source)
+                             if self.compiler else self._lib)
         except cabi.CompilationError as error:
             raise ParameterError(*error.args) from error
         if self.chunks < 1:

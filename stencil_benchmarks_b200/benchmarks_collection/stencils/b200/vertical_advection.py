@@ -53,7 +53,7 @@ class VerticalAdvectionMixin(StencilMixin):
             return (_vp * n)(*[pointers[c + suffix] for c, _, _ in components])
 
         # one sweep for all components: they share wcon, which is read from HBM once
-        self._lib.sb200_vadv_components(
+        self._kernels.sb200_vadv_components(
             self._dtype_code, n, table("stage"), table("pos"), table("tens"), table("tensstage"),
             (ctypes.c_int * n)(*[i for _, i, _ in components]),
             (ctypes.c_int * n)(*[j for _, _, j in components]),

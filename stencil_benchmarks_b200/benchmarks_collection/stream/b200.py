@@ -23,6 +23,10 @@ class Native(Benchmark):
     ntimes = Parameter("number of runs", 10)
     dtype = Parameter("data type in NumPy format, e.g. float32 or float64", "float64")
     verify = Parameter("verify results", True)
+    compiler = Parameter(
+        "compiler path: if given, the kernels are compiled at setup() through the reference's "
+        "tools.compilation path (stream/cuda_hip.py:88-94); empty: the prebuilt library", "")
+    compiler_flags = Parameter("additional compiler flags (with `compiler`)", "")
     device = Parameter("CUDA device ordinal", 0)
 
     #: arrays are padded to whole 128-byte lines (the reference pads to
@@ -45,6 +49,8 @@ class Native(Benchmark):
         self.array_size = -(-self.array_size // elements) * elements
         try:
             self._lib = capi.library()
+            self._kernels = (capi.jit_library(self.compiler, self.compiler_flags, "stream.cu")
+                             if self.compiler else self._lib)
         except cabi.CompilationError as error:
             raise ParameterError(*error.args) from error
 
@@ -52,7 +58,7 @@ class Native(Benchmark):
         try:
             capi.require_device()
             self._lib.sb200_set_device(self.device)
-            output = self._lib.sb200_stream_run(
+            output = self._kernels.sb200_stream_run(
                 self._dtype_code, self.array_size, self.ntimes, int(self.verify)
             )
         except cabi.ExecutionError as error:

@@ -115,6 +115,64 @@ def library() -> cabi.Library:
     return lib
 
 
+class TypedLibrary:
+    """A JIT-compiled library (the reference's ``GnuLibrary`` or the stand-alone mirror) whose
+    calls carry the prototypes of include/sbench_b200.h: both wrappers take ``argtypes=`` per call
+    (compilation.py:155-160), so int64 / double / pointer arguments are converted correctly."""
+
+    def __init__(self, library):
+        self.library = library
+
+    def __getattr__(self, name):
+        function = getattr(self.library, name)
+        argtypes = PROTOTYPES[name][1]
+        return lambda *args: function(*args, argtypes=argtypes)
+
+
+_JIT_CACHE = {}
+
+
+def jit_library(compiler, compiler_flags, source):
+    """Compile one kernel family at ``setup()`` the way the reference's backends do
+    (cuda_hip/mixin.py:60-84): source string -> ``tools.compilation.GnuLibrary`` -> ctypes handle.
+
+    The source is csrc/runtime.cu + csrc/<source> as one translation unit; the command is
+    ``<compiler> -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo <flags>``.
+    With the reference package importable its own ``GnuLibrary`` compiles and loads (source kept
+    under ./benchmarks_source_code, nvcc flags appended: compilation.py:125-153); otherwise the
+    mirror in tools/cabi.py does the same.  One compilation per (compiler, flags, source) and process.
+    """
+    import shlex
+    import tempfile
+
+    key = (compiler, compiler_flags, source)
+    if key in _JIT_CACHE:
+        return _JIT_CACHE[key]
+    code = "".join(f'#include "{ROOT / "csrc" / name}"\n' for name in ("runtime.cu", source))
+    command = [compiler, "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]
+    command += shlex.split(compiler_flags or "")
+    try:
+        from stencil_benchmarks.tools import compilation
+    except ImportError:
+        compilation = None
+    if compilation is not None:
+        try:
+            library = compilation.GnuLibrary(code, command, extension=".cu")
+        except compilation.CompilationError as error:
+            raise cabi.CompilationError(*error.args) from error
+        except FileNotFoundError as error:
+            raise cabi.CompilationError(f"compiler not found: {compiler}") from error
+    else:
+        directory = pathlib.Path(tempfile.mkdtemp(prefix="sb200_jit_"))
+        (directory / "source.cu").write_text(code)
+        try:
+            library = cabi.compile_library([directory / "source.cu"], directory / "library.so", command)
+        except FileNotFoundError as error:
+            raise cabi.CompilationError(f"compiler not found: {compiler}") from error
+    _JIT_CACHE[key] = TypedLibrary(library)
+    return _JIT_CACHE[key]
+
+
 def dtype_code(dtype) -> int:
     dtype = np.dtype(dtype)
     if dtype == np.float32:

@@ -93,6 +93,9 @@ def test_reference_run_and_oracle_judge_the_gpu_kernels(tmp_path):
         ("vadv", dict(domain=(200, 17, 160))),                      # BASELINE level count
         ("vadv", dict(domain=(96, 24, 40), all_components=True)),
         ("vadv", dict(domain=(33, 9, 12), coefficients="global")),
+        # kernels compiled at setup() through the reference's tools.compilation.GnuLibrary
+        ("hdiff", dict(domain=(300, 40, 5), compiler="nvcc")),
+        ("vadv", dict(domain=(130, 20, 30), compiler="nvcc")),
     ]
     result = run(VERIFY, tmp_path, json.dumps(cases))
     assert result.returncode == 0, result.stdout + result.stderr

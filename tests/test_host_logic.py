@@ -75,6 +75,23 @@ def test_failed_call_raises_with_stderr_message():
         lib.sb200_stream_run(7, 16, 2, 0)
 
 
+def test_kernels_compile_at_setup_like_the_reference_backends(tmp_path, monkeypatch):
+    """`compiler=...`: source string -> compile -> ctypes handle at setup() (cuda_hip/mixin.py:60-84);
+    compilation problems are ParameterErrors; calls carry the header's prototypes."""
+    monkeypatch.chdir(tmp_path)  # GnuLibrary keeps its sources under ./benchmarks_source_code
+    bench = vertical_advection.Thomas(domain=(16, 8, 4), compiler="nvcc", **CPU)
+    assert isinstance(bench._kernels, capi.TypedLibrary) and bench._kernels is not bench._lib
+    with pytest.raises((cabi.ExecutionError, RuntimeError), match="null component table"):
+        bench._kernels.sb200_vadv_components(capi.F64, 1, None, None, None, None, None, None, None, None, None,
+                                             4, 4, 1, 1, 8, 64, 0, 0, None, None)
+    again = vertical_advection.Thomas(domain=(8, 8, 4), compiler="nvcc", **CPU)
+    assert again._kernels is bench._kernels  # one compilation per process
+    with pytest.raises(benchmark.ParameterError, match="error"):
+        vertical_advection.Thomas(domain=(8, 8, 4), compiler="nvcc", compiler_flags="-Dint=", **CPU)
+    with pytest.raises(benchmark.ParameterError, match="not found"):
+        vertical_advection.Thomas(domain=(8, 8, 4), compiler="/no/such/nvcc", **CPU)
+
+
 def test_no_device_means_error_not_fallback():
     if capi.device_count() > 0:
         pytest.skip("a GPU is present")

@@ -71,3 +71,27 @@ def test_sbench_cli_lists_the_backend(reference_path):
         assert option in fused.stdout
     stream = run(code, reference_path, "stream", "b200", "native", "--help")
     assert stream.returncode == 0 and "--array-size" in stream.stdout
+
+
+def test_jit_goes_through_the_reference_gnulibrary(reference_path, tmp_path):
+    """With the reference importable, `compiler=nvcc` compiles the kernels through ITS
+    tools.compilation.GnuLibrary (source kept under ./benchmarks_source_code, compilation.py:130-137)."""
+    code = """
+import pathlib
+import stencil_benchmarks.tools.compilation as compilation
+from stencil_benchmarks_b200 import capi
+from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+bench = horizontal_diffusion.Fused(domain=(16, 12, 4), pinned=False, verify=False, compiler="nvcc")
+assert isinstance(bench._kernels.library, compilation.GnuLibrary)
+sources = list(pathlib.Path("benchmarks_source_code").glob("*.cu"))
+assert len(sources) == 1 and "hdiff.cu" in sources[0].read_text()
+try:
+    bench._kernels.sb200_hdiff(1, None, None, None, 0, 4, 4, 1, 8, 64, 0, None, None)
+except compilation.ExecutionError as error:
+    print("reference ExecutionError:", str(error).strip())
+"""
+    env = dict(os.environ, PYTHONPATH=f"{reference_path}:{ROOT}")
+    result = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                            timeout=300, cwd=str(tmp_path))
+    assert result.returncode == 0, result.stderr
+    assert "reference ExecutionError: sb200_hdiff: domain must be positive" in result.stdout
