@@ -134,6 +134,13 @@ uint64_t sb200_launch_count(void);
 /* STREAM (replaces `run()` of sb/bc/stream/cuda_hip.j2:179-288)       */
 /* ------------------------------------------------------------------ */
 
+/* Launch shape of the STREAM kernels for the calls that follow (the reference bakes these into
+ * its template: `block_size`, `unroll_factor`, `vector_size`, `streaming_loads/stores`,
+ * sb/bc/stream/cuda_hip.py:44-66).  0 (streaming: negative) keeps the measured default of that
+ * setting: 512 threads, 4 vectors per thread, 16-byte vectors, streaming (.cs) accesses.
+ * vector_bytes is 16 or 32 (one LDG.E.128 or LDG.E.ENL2.256 per vector). */
+int sb200_stream_configure(int block_size, int unroll_factor, int vector_bytes, int streaming);
+
 /* Full McCalpin-style run on device arrays owned by the library: init
  * (a=1, b=2, c=0), `ntimes` rounds of copy/scale/add/triad each timed with
  * events, iteration 0 discarded, table printed to stdout in the reference's

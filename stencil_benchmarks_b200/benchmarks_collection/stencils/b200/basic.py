@@ -2,8 +2,8 @@
 
 Counterparts of the reference classes in
 stencil_benchmarks/benchmarks_collection/stencils/cuda_hip/basic.py:101-132; the
-loop kind / block-size parameters of the reference (basic.py:44-48) have no
-meaning for the fixed sm_100a kernels and are not offered.
+loop kind / block-size parameters of the reference (basic.py:44-48) are accepted
+for script compatibility and have no effect on the fixed sm_100a kernels.
 """
 
 from .... import capi
@@ -15,6 +15,10 @@ _ALIGNMENT = Parameter("data alignment in bytes", 128)
 
 
 class BasicStencilMixin(StencilMixin):
+    loop = Parameter("loop kind (no effect)", "1D", choices=["1D", "3D"])
+    block_size = Parameter("block size (no effect)", (1024, 1, 1))
+    threads_per_block = Parameter("threads per block (no effect)", (0, 0, 0))
+
     field_roles = {"inp": "in", "out": "out"}
     kernel_source = "basic.cu"
     kind = capi.BASIC_EMPTY

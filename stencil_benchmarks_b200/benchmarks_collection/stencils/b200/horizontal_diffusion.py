@@ -16,6 +16,8 @@ from .mixin import StencilMixin, _vp
 
 
 class HorizontalDiffusionMixin(StencilMixin):
+    block_size = Parameter("block size of the reference's templates (no effect)", (32, 8, 1))
+
     field_roles = {"inp": "in", "coeff": "in", "out": "out"}
     kernel_source = "hdiff.cu"
     j_reach = 2

@@ -48,6 +48,10 @@ class StencilMixin(Benchmark):
     print_code = Parameter("print the CUDA source of the kernel", False)
     dry_runs = Parameter("kernel dry-runs before the measurement", 0)
     timers = Parameter("timer type", default="gpu", choices=["gpu", "wall"])
+    # tuning parameters of the reference's templates (cuda_hip/mixin.py:58 and the per-stencil
+    # mixins): accepted so that scripts written for `stencils cuda-hip ...` run unchanged.  The
+    # hand-written kernels have fixed, measured launch shapes; these have no effect.
+    index_type = Parameter("index data type (no effect)", "std::ptrdiff_t")
     # the fast (128-bit) kernels need an aligned interior origin and aligned rows
     alignment = Parameter("data alignment in bytes", 128)
     # new

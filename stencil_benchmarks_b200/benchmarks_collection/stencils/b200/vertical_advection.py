@@ -17,6 +17,9 @@ from .mixin import StencilMixin, _vp
 
 
 class VerticalAdvectionMixin(StencilMixin):
+    block_size = Parameter("block size of the reference's templates (no effect)", (32, 1))
+    unroll_factor = Parameter("unrolling of the vertical loop in the reference's templates (no effect)", -1)
+
     kernel_source = "vadv.cu"
     coefficients = Parameter(
         "where the eliminated Thomas coefficients live between the sweeps",

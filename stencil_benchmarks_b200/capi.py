@@ -67,6 +67,7 @@ PROTOTYPES = {
     "sb200_synchronize": (_i, [_vp]),
     "sb200_flush_l2": (_i, [_vp]),
     "sb200_launch_count": (_u64, []),
+    "sb200_stream_configure": (_i, [_i, _i, _i, _i]),
     "sb200_stream_run": (_i, [_i, _u64, _i, _i]),
     "sb200_stream_op": (_i, [_i, _i, _vp, _vp, _vp, _u64, ctypes.c_double, _i, _dp, _vp]),
     "sb200_basic": (_i, [_i, _i, _vp, _vp] + _geom + [_i, _i, _i, _dp, _vp]),

@@ -180,8 +180,15 @@ struct StreamConfig {
   int streaming = 1;
 };
 
+// sb200_stream_configure: explicit settings of the calling benchmark (0 = keep the default)
+StreamConfig g_stream_override{0, 0, 0, -1};
+
 StreamConfig stream_config() {
   StreamConfig cfg;
+  if (g_stream_override.block > 0) cfg.block = g_stream_override.block;
+  if (g_stream_override.unroll > 0) cfg.unroll = g_stream_override.unroll;
+  if (g_stream_override.vector_bytes > 0) cfg.vector_bytes = g_stream_override.vector_bytes;
+  if (g_stream_override.streaming >= 0) cfg.streaming = g_stream_override.streaming;
   if (const char* env = std::getenv("SB200_STREAM_CFG")) {
     int b, u, v, s;
     if (std::sscanf(env, "%d,%d,%d,%d", &b, &u, &v, &s) == 4) {
@@ -427,6 +434,17 @@ int stream_run(uint64_t n, int ntimes, int verify) {
 using namespace sb200;
 
 extern "C" {
+
+int sb200_stream_configure(int block_size, int unroll_factor, int vector_bytes, int streaming) {
+  if (block_size != 0 && (block_size < 32 || block_size > 1024 || block_size % 32))
+    return fail("sb200_stream_configure: block size must be a multiple of 32 in [32, 1024]");
+  if (unroll_factor != 0 && unroll_factor != 1 && unroll_factor != 2 && unroll_factor != 4 && unroll_factor != 8)
+    return fail("sb200_stream_configure: unroll factor must be 1, 2, 4 or 8");
+  if (vector_bytes != 0 && vector_bytes != 16 && vector_bytes != 32)
+    return fail("sb200_stream_configure: vectors are 16 or 32 bytes wide");
+  g_stream_override = StreamConfig{block_size, unroll_factor, vector_bytes, streaming < 0 ? -1 : (streaming != 0)};
+  return 0;
+}
 
 int sb200_stream_run(int dtype, uint64_t array_size, int ntimes, int verify) {
   if (dtype == SB200_F64) return stream_run<double>(array_size, ntimes, verify);

@@ -262,7 +262,8 @@ def _time_loop_worker(rank, world, port, domain, steps, results):
         halo = (3, 3, 3)
         rng = np.random.default_rng(33)
         shape = tuple(d + 2 * h for d, h in zip(domain, halo))
-        g_inp, g_coeff = np.asfortranarray(rng.random(shape)), np.asfortranarray(rng.random(shape))
+        # a stable time step: coeff <= 1/32 (with U[0,1) the scheme amplifies rounding ~4x per sweep)
+        g_inp, g_coeff = np.asfortranarray(rng.random(shape)), np.asfortranarray(rng.random(shape) * 0.025)
         start, ny = distributed.split_rows(ny_global, world)[rank]
         bench = horizontal_diffusion.Fused(domain=(nx, ny, nz), halo=halo, verify=False, device=rank)
         data = bench.data()

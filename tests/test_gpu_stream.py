@@ -89,3 +89,19 @@ def test_launch_counter_counts():
     bench = stream.Native(array_size=1 << 16, ntimes=2)
     bench.run()
     assert capi.launch_count() - before >= 1 + 2 * 4
+
+
+@pytest.mark.parametrize("shape", [dict(block_size=256, vector_size=4, unroll_factor=2),
+                                   dict(block_size=1024, vector_size=2, unroll_factor=1),
+                                   dict(block_size=128, vector_size=4, unroll_factor=8, streaming_loads=False,
+                                        streaming_stores=False)])
+def test_native_with_the_reference_tuning_parameters(shape):
+    """block_size / vector_size / unroll_factor / streaming_* of `stream cuda-hip native`
+    (cuda_hip.py:44-66) select the launch shape; every shape verifies."""
+    bench = stream.Native(array_size=1 << 24, ntimes=3, dtype="float64", **shape)
+    try:
+        results = bench.run()  # raises ExecutionError if the closed-form verification fails
+    finally:
+        capi.library().sb200_stream_configure(0, 0, 0, -1)
+    assert [r["name"] for r in results] == ["copy", "scale", "add", "triad"]
+    assert all(r["bandwidth"] > 1e5 for r in results)

@@ -92,6 +92,30 @@ def test_kernels_compile_at_setup_like_the_reference_backends(tmp_path, monkeypa
         vertical_advection.Thomas(domain=(8, 8, 4), compiler="/no/such/nvcc", **CPU)
 
 
+def test_parameters_of_cuda_hip_scripts_are_accepted():
+    """Keyword sets the reference's collection scripts pass to its cuda_hip classes
+    (scripts/sbench_h100_collection.py:72-152) construct the B200 classes unchanged."""
+    common = dict(backend="cuda", verify=False, dry_runs=1, alignment=128, dtype="float32", pinned=False)
+    assert basic.Copy(loop="3D", block_size=(128, 2, 1), halo=(1, 1, 1), domain=(32, 32, 8), **common).loop == "3D"
+    basic.Laplacian(loop="1D", block_size=(1024, 1, 1), threads_per_block=(0, 0, 0), domain=(32, 32, 8), **common)
+    horizontal_diffusion.Fused(block_size=(28, 8, 2), index_type="int", domain=(32, 32, 8), **common)
+    vertical_advection.Thomas(block_size=(128, 1), unroll_factor=28, domain=(32, 32, 8), **common)
+    native = stream.Native(array_size=1000, block_size=256, vector_size=4, unroll_factor=2, axis="x",
+                           explicit_vectorization=True, launch_bounds=True, index_type="std::size_t",
+                           streaming_stores=True, streaming_loads=True, dtype="float64")
+    assert native.array_size % 16 == 0
+    with pytest.raises(benchmark.ParameterError, match="vector_size"):
+        stream.Native(array_size=1000, vector_size=3)
+    with pytest.raises(benchmark.ParameterError, match="unroll_factor"):
+        stream.Native(array_size=1000, unroll_factor=3)
+    with pytest.raises(benchmark.ParameterError, match="block_size"):
+        stream.Native(array_size=1000, block_size=100)
+    with pytest.raises(benchmark.ParameterError, match="together"):
+        stream.Native(array_size=1000, streaming_loads=False)
+    with pytest.raises(benchmark.ParameterError):
+        stream.Native(array_size=1000, load_cache_modifier="cg")
+
+
 def test_no_device_means_error_not_fallback():
     if capi.device_count() > 0:
         pytest.skip("a GPU is present")
