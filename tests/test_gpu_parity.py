@@ -38,6 +38,17 @@ def close(result, expected, dtype):
     return np.allclose(result, expected, **stencils.tolerances(dtype))
 
 
+# float32 vertical advection: the reference's own OpenMP backend fails the reference tolerance on
+# 0.026-0.03 % of the points of U[0,1) inputs (344-702 of 1.3-2.6 M); the B200
+# kernels may miss it on at most ten times that fraction (and never on more than a handful of
+# points of a tiny domain)
+VADV_F32_MISMATCH = 3e-3
+
+
+def f32_vadv_ok(bad):
+    return bad.sum() <= max(3, VADV_F32_MISMATCH * bad.size)
+
+
 def check_inputs_untouched(bench, before, written):
     after = bench.data()
     for name, field in zip(bench.args, after):
@@ -88,9 +99,10 @@ def test_golden(case, alignment):
         expected = g["expected_" + name]
         if case.startswith("vadv") and dtype == "float32":
             # float32 vadv is ill-conditioned on U[0,1) inputs; the reference's own
-            # OpenMP backend fails its tolerance too.  Require agreement on all but a tiny fraction.
+            # OpenMP backend misses its tolerance on about 0.03 % of the points.  Policy: at most ten
+            # times that fraction (VADV_F32_MISMATCH).
             bad = ~np.isclose(result, expected, **stencils.tolerances(dtype))
-            assert bad.mean() < 1e-2, f"{case}:{name}: {bad.sum()} of {bad.size} points differ"
+            assert f32_vadv_ok(bad), f"{case}:{name}: {bad.sum()} of {bad.size} points differ"
         else:
             assert close(result, expected, dtype), (
                 f"{case}:{name}: max abs err {np.abs(result - expected).max()}")
@@ -181,7 +193,7 @@ def test_vadv_random(domain, halo, dtype, all_components):
         if dtype == "float64":
             assert not bad.any(), f"{c}: {bad.sum()} of {bad.size} points differ"
         else:  # float32 policy, SURVEY.md §8c: ill-conditioned columns, tiny mismatch fraction allowed
-            assert bad.mean() < 1e-2, f"{c}: {bad.sum()} of {bad.size} points differ"
+            assert f32_vadv_ok(bad), f"{c}: {bad.sum()} of {bad.size} points differ"
     check_inputs_untouched(bench, before, [c + "tensstage" for c in components])
 
 
@@ -371,14 +383,28 @@ def test_hdiff_short_marches(ny):
         assert close(bench.data().out[inner], expected, dtype)
 
 
-def test_basic_full_size_float32():
-    bench = basic.Laplacian(domain=(1024, 1024, 80), halo=(1, 1, 1), dtype="float32", verify=False, seed=3)
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("kind", ["copy", "onesided_i", "onesided_k", "symmetric_j", "laplacian_ij", "laplacian_ijk"])
+def test_basic_full_size(kind, dtype):
+    """BASELINE.json configs[2]: the basic stencils at 1024x1024x80, both dtypes, against the C oracle."""
+    common = dict(domain=(1024, 1024, 80), halo=(1, 1, 1), dtype=dtype, verify=False, seed=3)
+    expected_call = {
+        "copy": (basic.Copy, {}, lambda i, o, h: native.copy(i, o, h)),
+        "onesided_i": (basic.OnesidedAverage, dict(axis=0), lambda i, o, h: native.average(i, o, h, 0, False)),
+        "onesided_k": (basic.OnesidedAverage, dict(axis=2), lambda i, o, h: native.average(i, o, h, 2, False)),
+        "symmetric_j": (basic.SymmetricAverage, dict(axis=1), lambda i, o, h: native.average(i, o, h, 1, True)),
+        "laplacian_ij": (basic.Laplacian, {}, lambda i, o, h: native.laplacian(i, o, h, (True, True, False))),
+        "laplacian_ijk": (basic.Laplacian, dict(along_z=True),
+                          lambda i, o, h: native.laplacian(i, o, h, (True, True, True))),
+    }
+    cls, kwargs, oracle = expected_call[kind]
+    bench = cls(**common, **kwargs)
     data = bench.data()
     bench.run()
     expected = bench.empty_field()
-    native.laplacian(data.inp, expected, bench.halo, (True, True, False))
+    oracle(data.inp, expected, tuple(bench.halo))
     inner = bench.inner_slice()
-    assert close(data.out[inner], expected[inner], "float32")
+    assert close(data.out[inner], expected[inner], dtype)
 
 
 @pytest.mark.parametrize("all_components", [False, True])
@@ -446,3 +472,25 @@ def test_partitioned_class_on_one_gpu(dtype):
     inner = bench.inner_slice()
     assert close(data.out[inner], expected[inner], dtype)
     assert np.array_equal(data.inp, before[0]) and np.array_equal(data.coeff, before[1])
+
+
+@pytest.mark.gpu
+def test_vadv_float32_mismatch_fraction_is_of_the_reference_backends_order():
+    """256x256x160 float32 on U[0,1) inputs: the fraction of points outside the reference tolerance
+    stays within VADV_F32_MISMATCH; the measured fraction is recorded for DESIGN.md."""
+    import json
+
+    bench = vertical_advection.Thomas(domain=(256, 256, 160), dtype="float32", verify=False, seed=17)
+    before = snapshot(bench)
+    bench.run()
+    inner = bench.inner_slice()
+    expected = stencils._vadv_component(before["ustage"], before["upos"], before["utens"], before["utensstage"],
+                                        before["wcon"], tuple(bench.halo), 1, 0)[inner]
+    bad = ~np.isclose(bench.data().utensstage[inner], expected, **stencils.tolerances("float32"))
+    fraction = float(bad.mean())
+    out = pathlib.Path(__file__).parent.parent / "gpurun_out"
+    if out.is_dir():
+        (out / "vadv_f32_mismatch.json").write_text(json.dumps(
+            dict(domain=[256, 256, 160], points=int(bad.size), mismatching=int(bad.sum()), fraction=fraction,
+                 bound=VADV_F32_MISMATCH, reference_openmp_fraction="0.026-0.03 % (SURVEY.md 8c)")))
+    assert fraction <= VADV_F32_MISMATCH, f"{bad.sum()} of {bad.size} points differ"
