@@ -265,9 +265,11 @@ int sb200_hdiff_peer(int dtype, const void* inp, const void* coeff, void* out,
  * last rows wait (ld.acquire.sys) until the neighbour's sweep m-1 has finished with the rows both
  * touch, and tell the neighbours when they are done themselves (red.release.sys into the
  * neighbours' memory over NVLink); every other CTA runs unhindered, the host is not involved.
- *   arrived        this slab's counters, two zero-initialised uint32 in its own device memory:
- *                  [0] is pushed by the lower, [1] by the upper neighbour
- *   notify_lower   address of the LOWER neighbour's arrived[1], mapped into this process
+ *   arrived        this slab's counters, 2 * nz zero-initialised uint32 in its own device memory:
+ *                  [k] is pushed by the lower, [nz + k] by the upper neighbour (one counter per
+ *                  level: a CTA waits for the neighbour CTAs of its own level only)
+ *   notify_lower   address of the LOWER neighbour's arrived[nz] (the half its upper neighbour
+ *                  pushes), mapped into this process
  *   notify_upper   address of the UPPER neighbour's arrived[0]
  *   step           m = 0, 1, 2, ...: index of this sweep in the loop; every slab calls with the
  *                  same sequence.  The fields, their neighbours and the domain must stay the same

@@ -225,21 +225,26 @@ struct PeerMaps {
 };
 
 // Time loop over J slabs (inp and out swap roles every step): what orders the sweeps of
-// neighbouring GPUs.  The CTAs of a slab's first / last segment ("edge CTAs") are the only ones
-// that read a neighbour's rows and the only ones whose output rows a neighbour reads.  When an edge
-// CTA has stored its rows, each of its four consumer warps adds 1 to a counter in the neighbour's
-// memory (red.release.sys over NVLink) -- after sweep m-1 the counter stands at m * (edge warps per
-// sweep).  The producer of an edge CTA of sweep m spins on the LOCAL counter its neighbour pushes
+// neighbouring GPUs.  "Edge CTAs" are the CTAs that read a neighbour's rows and whose output rows
+// a neighbour reads: the first segment of every (i tile, level) towards the lower neighbour, and
+// towards the upper one every segment that ends at row ny-1 or ny (the last one, and the one
+// before it when the last segment is a single row).  When an edge CTA has stored its rows, each of
+// its four consumer warps adds 1 to the counter of its LEVEL in the neighbour's memory
+// (red.release.sys over NVLink) -- after sweep m-1 a level's counter stands at m * (edge warps per
+// level and sweep).  The producer of an edge CTA of sweep m spins on the LOCAL counter of its level
 // (ld.acquire.sys) until it has reached that value before it issues its first load: then the
 // neighbour's rows of the field it is about to read are complete (they were written in the
 // neighbour's sweep m-1), and the neighbour no longer reads the rows this CTA is about to overwrite
-// (it read them in its sweep m-1).  No host involvement, no extra launch; CTAs that are not on an
-// edge never look at a flag.  Sweeps of one GPU are ordered by the stream, so a waiting CTA only
-// ever depends on sweeps that do not depend on it.
+// (it read them in its sweep m-1).  Counters are per level, so a CTA waits for the handful of
+// neighbour CTAs it really depends on -- which finished most of a sweep ago -- and not for the
+// neighbour's whole sweep.  No host involvement, no extra launch; CTAs that are not on an edge never
+// look at a counter.  Sweeps of one GPU are ordered by the stream, so a waiting CTA only ever
+// depends on sweeps that do not depend on it.
 struct StepFlags {
-  const unsigned int* arrived[2];  // local counters: [0] pushed by the lower, [1] by the upper neighbour
-  unsigned int* notify[2];         // the neighbours' counters this slab pushes: [0] lower, [1] upper
-  unsigned int wait_value;         // m * edge warps per sweep; 0: nothing to wait for
+  const unsigned int* arrived;   // local counters: [k] pushed by the lower, [levels + k] by the upper neighbour
+  unsigned int* notify[2];       // the neighbours' counters this slab pushes: [0] lower (its upper half), [1] upper
+  unsigned int wait_value[2];    // what a level's counter shows once the neighbour's previous sweep is through it
+  int levels;
 };
 
 __device__ __forceinline__ void wait_for_neighbour(const unsigned int* counter, unsigned int value) {
@@ -310,12 +315,14 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
         }
       }
       const int c0 = it / (8 / int(sizeof(T)));  // tile origin in 8-byte elements
-      if (PEER && flags.wait_value != 0) {
+      if (PEER && (flags.wait_value[0] | flags.wait_value[1]) != 0) {
         // time loop: an edge CTA starts once the neighbour's previous sweep has finished with the
         // rows both touch; the async proxy (TMA) must not run ahead of the acquire
-        if (peer.has_lower && jb == 0) wait_for_neighbour(flags.arrived[0], flags.wait_value);
-        if (peer.has_upper && je == ny) wait_for_neighbour(flags.arrived[1], flags.wait_value);
-        asm volatile("fence.proxy.async;" ::: "memory");
+        const bool lower_edge = peer.has_lower && jb == 0;
+        const bool upper_edge = peer.has_upper && je >= ny - 1;
+        if (lower_edge) wait_for_neighbour(flags.arrived + k, flags.wait_value[0]);
+        if (upper_edge) wait_for_neighbour(flags.arrived + flags.levels + k, flags.wait_value[1]);
+        if (lower_edge || upper_edge) asm volatile("fence.proxy.async;" ::: "memory");
       }
       for (int n = 0; n < nstages; ++n) {
         const int slot = n % S;
@@ -437,13 +444,15 @@ __global__ void __launch_bounds__(tmacfg::kThreads, 4)
     // time loop: tell the neighbours that this edge CTA's rows are written (and that it no longer
     // reads theirs); the release at system scope covers the whole warp's stores
     const bool lower_edge = peer.has_lower && jb == 0 && flags.notify[0] != nullptr;
-    const bool upper_edge = peer.has_upper && je == ny && flags.notify[1] != nullptr;
+    const bool upper_edge = peer.has_upper && je >= ny - 1 && flags.notify[1] != nullptr;
     if (lower_edge || upper_edge) {
       __threadfence_system();
       __syncwarp();
       if ((threadIdx.x & 31) == 0) {
-        if (lower_edge) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flags.notify[0]) : "memory");
-        if (upper_edge) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flags.notify[1]) : "memory");
+        if (lower_edge)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flags.notify[0] + k) : "memory");
+        if (upper_edge)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flags.notify[1] + k) : "memory");
       }
     }
   }
@@ -610,11 +619,24 @@ int launch_hdiff_tma_rs(const T* inp, const T* coeff, T* out, int64_t nx, int64_
       ensure_dynamic_smem(hdiff_tma_kernel<T, R, S, true>, smem, attr_peer))
     return 1;
   *used = true;
-  StepFlags flags{{nullptr, nullptr}, {nullptr, nullptr}, 0};
+  StepFlags flags{nullptr, {nullptr, nullptr}, {0, 0}, int(nz)};
   if (step_flags != nullptr) {
     flags = *step_flags;
-    // every edge CTA notifies once per consumer warp: xtiles * levels CTAs per edge and sweep
-    flags.wait_value = step * unsigned(xtiles * nz) * unsigned(tmacfg::kConsumers / 32);
+    flags.levels = int(nz);
+    // every edge CTA notifies once per consumer warp.  Towards its upper neighbour a slab has
+    // one edge segment per (i tile, level), or two when its last segment is a single row -- what
+    // this slab waits for from BELOW is therefore a property of the lower neighbour's tiling.
+    const unsigned per_segment = unsigned(xtiles) * unsigned(tmacfg::kConsumers / 32);
+    unsigned lower_segments = 1;
+    if (inp_lower != nullptr) {
+      HdiffTiling theirs;
+      int64_t unused = 0;
+      if (!hdiff_make_tiling(R, xtiles, ny_lower, nz, jt_request, theirs, unused))
+        return fail("sb200_hdiff_step: the lower neighbour's slab is too large for the launch grid");
+      if (theirs.segments > 1 && (ny_lower - 1) % theirs.jt == 0) lower_segments = 2;
+    }
+    flags.wait_value[0] = step * per_segment * lower_segments;
+    flags.wait_value[1] = step * per_segment;
   }
   auto launch = [&] {
     if (with_peers)
@@ -758,11 +780,11 @@ extern "C" int sb200_hdiff_step(int dtype, const void* inp, const void* coeff, v
       (inp_upper != nullptr && notify_upper == nullptr))
     return fail("sb200_hdiff_step: a slab with neighbours needs its own counters and theirs");
   StepFlags flags;
-  flags.arrived[0] = arrived;
-  flags.arrived[1] = arrived + 1;
+  flags.arrived = arrived;
   flags.notify[0] = inp_lower != nullptr ? notify_lower : nullptr;
   flags.notify[1] = inp_upper != nullptr ? notify_upper : nullptr;
-  flags.wait_value = 0;
+  flags.wait_value[0] = flags.wait_value[1] = 0;
+  flags.levels = int(nz);
   return hdiff_peer_entry("sb200_hdiff_step", dtype, inp, coeff, out, inp_lower, ny_lower, sz_lower, inp_upper,
                           ny_upper, sz_upper, &flags, step, nx, ny, nz, sx, sy, sz, 0, time, stream);
 }

@@ -339,6 +339,19 @@ __device__ __forceinline__ void rescale(float& p, float& r, float& q) {
   q *= f;
 }
 
+// Store guarded by a predicate instead of a branch: the k-sequential loop has one warp per
+// scheduler, so every BSSY / BRA / BSYNC around a store is issue latency on the critical path.
+__device__ __forceinline__ void store_if(bool valid, double* p, double v) {
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f64 [%0], %1; }" ::"l"(p), "d"(v),
+               "r"(int(valid))
+               : "memory");
+}
+__device__ __forceinline__ void store_if(bool valid, float* p, float v) {
+  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f32 [%0], %1; }" ::"l"(p), "f"(v),
+               "r"(int(valid))
+               : "memory");
+}
+
 // Forward state of the column a thread is eliminating.  c[k] = p/q and d[k] = r/q are kept as a
 // homogeneous triple: with a, b, cc, d0 the coefficients of level k (base.py:432-445),
 //     c[k] = cc / (b - c[k-1] a)            =>  p' = cc q,  q' = b q - a p
@@ -391,7 +404,7 @@ __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T
   T c_old, e_old;
   slot.load(r, c_old, e_old);
   z = e_old - c_old * z;
-  if (old_valid) *old_out = dtr_stage * z;
+  store_if(old_valid, old_out, dtr_stage * z);
   slot.store(r, c, e);
   f.pos_cur = v_pos; f.tens_cur = v_tens; f.tss_cur = v_tss;
 }
@@ -614,17 +627,16 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
         auto body = [&](auto kind_tag) {
           constexpr int KIND = decltype(kind_tag)::value;
           VadvCursor<T, KIND> slot(slots, pa, dp);
-          // output pointer of the old column: float64 schedules best when it is recomputed per
-          // level, float32 (issue bound) when it is carried (measured, profiles/vadv_tuning_r01.log)
-          constexpr bool kRecompute = sizeof(T) == 8;
-          T* out = old_base + int64_t(nz - 1 - s0) * sz;
+          // output pointers of the old column's four levels: one 64-bit product per chunk, the
+          // other three by subtraction (a product per level costs 8 integer instructions each)
+          T* outs[KD];
+          outs[0] = old_base + int64_t(nz - 1 - s0) * sz;
 #pragma unroll
-          for (int r = 0; r < KD; ++r) {
-            if (kRecompute) out = old_base + int64_t(nz - 1 - (s0 + r)) * sz;
+          for (int r = 1; r < KD; ++r) outs[r] = outs[r - 1] - sz;
+#pragma unroll
+          for (int r = 0; r < KD; ++r)
             vadv_step<T, false, KIND>(s0 + r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
-                                      slot, r, out, old_valid);
-            if (!kRecompute) out -= sz;
-          }
+                                      slot, r, outs[r], old_valid);
         };
         if (kind == 1)
           body(std::integral_constant<int, 1>{});

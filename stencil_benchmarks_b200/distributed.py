@@ -251,7 +251,7 @@ class TimeLoop:
     New with respect to the reference, which sweeps once per ``run()`` on one GPU.
     """
 
-    #: own allocation for the two counters: large enough that the CUDA allocator does not carve it
+    #: own allocation for the 2 x nz counters: large enough that the CUDA allocator does not carve it
     #: out of a block shared with other buffers (an IPC handle always maps a whole block)
     FLAG_BYTES = 2 << 20
 
@@ -305,8 +305,10 @@ class TimeLoop:
                 self.code, vp(self.interior[src]), vp(self.coeff), vp(self.interior[dst]),
                 vp(peers.lower), peers.ny_lower, peers.sz_lower, vp(peers.upper), peers.ny_upper, peers.sz_upper,
                 vp(self.flags.ptr),
-                vp(flags.lower + 4 if flags.lower is not None else None),   # lower neighbour's arrived[1]
-                vp(flags.upper if flags.upper is not None else None),       # upper neighbour's arrived[0]
+                # the lower neighbour's arrived[nz:] (pushed by its upper neighbour: this slab),
+                # the upper neighbour's arrived[:nz]
+                vp(flags.lower + 4 * int(self.geometry[2]) if flags.lower is not None else None),
+                vp(flags.upper if flags.upper is not None else None),
                 m, *self.geometry, None, vp(stream))
         if status != 0:
             raise RuntimeError(f"sweep {m} of the time loop failed (status {status}); see stderr")

@@ -302,7 +302,11 @@ def _time_loop_worker(rank, world, port, domain, steps, results, return_state=Fa
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("domain,steps", [((300, 64, 5), 7), ((512, 259, 3), 12), ((1100, 40, 9), 25)])
+@pytest.mark.parametrize("domain,steps", [((300, 64, 5), 7), ((512, 259, 3), 12), ((1100, 40, 9), 25),
+                                          # slabs of 16 n + 1 rows: the last march segment is a single
+                                          # row, so TWO segments per tile exchange rows with the upper
+                                          # neighbour
+                                          ((520, 66, 4), 20), ((300, 130, 2), 16)])
 def test_time_loop_orders_neighbouring_gpus(domain, steps):
     import torch.multiprocessing as mp
 
