@@ -170,7 +170,13 @@ def cuda_configurations():
 
 
 def build_cuda(captured, manifest):
-    """Render + cross-compile the reference's CUDA kernels (sm_100 SASS; runs on the GPU box)."""
+    """Render + cross-compile the reference's CUDA kernels (sm_100 SASS; runs on the GPU box).
+    Rendering goes through the reference's classes one by one; the nvcc runs are independent and
+    run a few at a time."""
+    import concurrent.futures
+    import os
+
+    jobs = []
     for name, cls, kwargs in cuda_configurations():
         try:
             bench = cls(**kwargs)
@@ -183,20 +189,28 @@ def build_cuda(captured, manifest):
         flags = [f for f in captured["command"][1:] if f not in ("-x", "cu")]
         command = [captured["command"][0], "-o", str(target), "-x", "cu", str(source)] + flags + [
             "-Xcompiler", "-shared", "-Xcompiler", "-fPIC"]
-        result = subprocess.run(command, capture_output=True, text=True)
-        if result.returncode != 0:
-            print(f"skipped {name}: does not compile for this configuration: "
-                  + result.stderr.strip().splitlines()[-1])
-            continue
-        manifest[name] = dict(
+        entry = dict(
             reference_class=f"{cls.__module__}.{cls.__name__}",
             kwargs={k: (list(v) if isinstance(v, tuple) else v) for k, v in kwargs.items()},
             args=list(bench.args), domain=list(bench.domain), halo=list(bench.halo),
             strides=[int(s) for s in bench.strides], alignment=int(bench.alignment), dtype=bench.dtype,
             data_size=int(bench.data_size), compile_flags=flags, libraries={"sm_100": target.name},
         )
-        print(f"built {name}: strides {manifest[name]['strides']}")
+        jobs.append((name, command, entry))
         del bench
+
+    def compile_one(job):
+        name, command, entry = job
+        return name, entry, subprocess.run(command, capture_output=True, text=True)
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(2, (os.cpu_count() or 2))) as pool:
+        for name, entry, result in pool.map(compile_one, jobs):
+            if result.returncode != 0:
+                print(f"skipped {name}: does not compile for this configuration: "
+                      + result.stderr.strip().splitlines()[-1])
+                continue
+            manifest[name] = entry
+            print(f"built {name}: strides {entry['strides']}")
 
 
 def main():

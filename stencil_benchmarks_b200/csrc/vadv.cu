@@ -339,17 +339,28 @@ __device__ __forceinline__ void rescale(float& p, float& r, float& q) {
   q *= f;
 }
 
-// Store guarded by a predicate instead of a branch: the k-sequential loop has one warp per
-// scheduler, so every BSSY / BRA / BSYNC around a store is issue latency on the critical path.
+// Store of one output value.  MODE 1: guarded by a predicate instead of a branch (the k-sequential
+// loop has one warp per scheduler, so every BSSY / BRA / BSYNC around a store is issue latency on
+// the critical path); no "memory" clobber: the kernel reads utensstage through TMA only, and a
+// compiler barrier per level would pin the shared-memory loads of the next level behind it.
+// MODE 0: the plain conditional store.
+template <int MODE>
 __device__ __forceinline__ void store_if(bool valid, double* p, double v) {
-  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f64 [%0], %1; }" ::"l"(p), "d"(v),
-               "r"(int(valid))
-               : "memory");
+  if (MODE == 1) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f64 [%0], %1; }" ::"l"(p), "d"(v),
+                 "r"(int(valid)));
+  } else if (valid) {
+    *p = v;
+  }
 }
+template <int MODE>
 __device__ __forceinline__ void store_if(bool valid, float* p, float v) {
-  asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f32 [%0], %1; }" ::"l"(p), "f"(v),
-               "r"(int(valid))
-               : "memory");
+  if (MODE == 1) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.global.f32 [%0], %1; }" ::"l"(p), "f"(v),
+                 "r"(int(valid)));
+  } else if (valid) {
+    *p = v;
+  }
 }
 
 // Forward state of the column a thread is eliminating.  c[k] = p/q and d[k] = r/q are kept as a
@@ -373,7 +384,7 @@ struct VadvForward {
 // One lock-step iteration: level s of the new column has arrived (values v_*), level k = s-1 is
 // eliminated and stored, after the old column's level nz-1-s has been back-substituted from the
 // same slot.  FIRST: s may be 0 (resolved at compile time in the peeled first chunk).
-template <class T, bool FIRST, int KIND>
+template <class T, bool FIRST, int KIND, int STORE = 0>
 __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T v_pos, T v_tens,
                                           T v_tss, T v_wsum, T& z, const VadvCursor<T, KIND>& slot, int r,
                                           T* old_out, bool old_valid) {
@@ -404,7 +415,7 @@ __device__ __forceinline__ void vadv_step(int s, VadvForward<T>& f, T v_stage, T
   T c_old, e_old;
   slot.load(r, c_old, e_old);
   z = e_old - c_old * z;
-  store_if(old_valid, old_out, dtr_stage * z);
+  store_if<STORE>(old_valid, old_out, dtr_stage * z);
   slot.store(r, c, e);
   f.pos_cur = v_pos; f.tens_cur = v_tens; f.tss_cur = v_tss;
 }
@@ -431,7 +442,7 @@ struct VadvComponents {
 // drawn back to back, so three CTAs sweep the same columns at the same time and the wcon tiles
 // (and the j+1 tiles of the v component, which are the next row's own tiles) are fetched from HBM
 // once and hit the L2 twice: one launch moves 16 fields' worth of HBM traffic, not 18.
-template <class T, int KD>
+template <class T, int KD, int STORE>
 __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
     vadv_onchip_kernel(const __grid_constant__ VadvMaps maps,
                        const __grid_constant__ VadvComponents<T> comps, unsigned int* __restrict__ counter,
@@ -606,7 +617,7 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
 #pragma unroll
         for (int r = 0; r < KD; ++r) {
           if (r < nz)
-            vadv_step<T, true, 2>(r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z, slot, r,
+            vadv_step<T, true, 2, STORE>(r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z, slot, r,
                                   old_base + int64_t(nz - 1 - r) * sz, old_valid);
         }
       }
@@ -627,16 +638,21 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
         auto body = [&](auto kind_tag) {
           constexpr int KIND = decltype(kind_tag)::value;
           VadvCursor<T, KIND> slot(slots, pa, dp);
-          // output pointers of the old column's four levels: one 64-bit product per chunk, the
-          // other three by subtraction (a product per level costs 8 integer instructions each)
-          T* outs[KD];
-          outs[0] = old_base + int64_t(nz - 1 - s0) * sz;
+          // output pointer of the old column.  STORE 0 (round 1): float64 schedules best when it is
+          // recomputed per level, float32 (issue bound) when it is carried
+          // (profiles/vadv_tuning_r01.log).  STORE 1: one 64-bit product per chunk, carried by
+          // subtraction, next to the predicated store (a product per level costs 8 integer
+          // instructions).  Computing all four pointers ahead of the chunk is slower in every
+          // combination (profiles/vadv_storepath_r02.log).
+          constexpr bool kRecompute = sizeof(T) == 8 && STORE == 0;
+          T* out = old_base + int64_t(nz - 1 - s0) * sz;
 #pragma unroll
-          for (int r = 1; r < KD; ++r) outs[r] = outs[r - 1] - sz;
-#pragma unroll
-          for (int r = 0; r < KD; ++r)
-            vadv_step<T, false, KIND>(s0 + r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
-                                      slot, r, outs[r], old_valid);
+          for (int r = 0; r < KD; ++r) {
+            if (kRecompute) out = old_base + int64_t(nz - 1 - (s0 + r)) * sz;
+            vadv_step<T, false, KIND, STORE>(s0 + r, f, v_stage[r], v_pos[r], v_tens[r], v_tss[r], v_wsum[r], z,
+                                             slot, r, out, old_valid);
+            if (!kRecompute) out -= sz;
+          }
         };
         if (kind == 1)
           body(std::integral_constant<int, 1>{});
@@ -654,7 +670,7 @@ __global__ void __launch_bounds__(vcfg::threads<T>(), 1)
         for (int s = s0; s < nz; ++s) {
           T v_stage, v_pos, v_tens, v_tss, v_wsum;
           fetch(stage, s - s0, v_stage, v_pos, v_tens, v_tss, v_wsum);
-          vadv_step<T, false, 2>(s, f, v_stage, v_pos, v_tens, v_tss, v_wsum, z, slot, s - s0,
+          vadv_step<T, false, 2, STORE>(s, f, v_stage, v_pos, v_tens, v_tss, v_wsum, z, slot, s - s0,
                                  old_base + int64_t(nz - 1 - s) * sz, old_valid);
         }
         release();
@@ -760,13 +776,18 @@ int launch_vadv_onchip(const VadvSystem<T>* systems, int ncomp, const T* wcon, i
       !tma::encode_3d(&maps.wcon_edge, type, wcon, nx + ishift, ny + jshift, nz, s1, s2, vcfg::edge_elems<T>(), 1,
                       KD))
     return 0;
+  // SB200_VADV_STORE (tuning aid): 0 = conditional stores, 1 = predicated stores + one pointer product per chunk
+  int store_mode = sizeof(T) == 8 ? 1 : 0;
+  if (const char* env = std::getenv("SB200_VADV_STORE")) store_mode = std::atoi(env) != 0;
   static std::atomic<uint64_t> attr_done{0};
   {
     int device = 0;
     SB200_CHECK(cudaGetDevice(&device));
     const uint64_t bit = uint64_t(1) << (device & 63);
     if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-      SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+      SB200_CHECK(cudaFuncSetAttribute(vadv_onchip_kernel<T, KD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
       attr_done.fetch_or(bit, std::memory_order_release);
     }
@@ -782,8 +803,12 @@ int launch_vadv_onchip(const VadvSystem<T>* systems, int ncomp, const T* wcon, i
       counter_ok = false;
       return;
     }
-    vadv_onchip_kernel<T, KD><<<grid, vcfg::threads<T>(), smem, stream>>>(
-        maps, comps, counter, int(nx), int(ny), int(nz), sy, sz, stages, paired);
+    if (store_mode)
+      vadv_onchip_kernel<T, KD, 1><<<grid, vcfg::threads<T>(), smem, stream>>>(
+          maps, comps, counter, int(nx), int(ny), int(nz), sy, sz, stages, paired);
+    else
+      vadv_onchip_kernel<T, KD, 0><<<grid, vcfg::threads<T>(), smem, stream>>>(
+          maps, comps, counter, int(nx), int(ny), int(nz), sy, sz, stages, paired);
     count_launch();
   };
   const int rc = timed(launch, dry_runs, time, stream);

@@ -172,13 +172,18 @@ def cuda_halo_exchange(rank, world_size, dtype, nx, ny, nz, hx, sy, sz, width, g
     def stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def checked(status, what):
+        # raw calls (no stdout/stderr capture on the hot path): a failed launch must not go unnoticed
+        if status != 0:
+            raise RuntimeError(f"{what} failed (status {status}); see stderr")
+
     def pack(field, j0, nrows, buffer):
-        lib.raw.sb200_pack_rows(code, ctypes.c_void_p(field), ctypes.c_void_p(buffer.data_ptr()),
-                                nx, nz, hx, sy, sz, j0, nrows, stream())
+        checked(lib.raw.sb200_pack_rows(code, ctypes.c_void_p(field), ctypes.c_void_p(buffer.data_ptr()),
+                                        nx, nz, hx, sy, sz, j0, nrows, stream()), "sb200_pack_rows")
 
     def unpack(field, j0, nrows, buffer):
-        lib.raw.sb200_unpack_rows(code, ctypes.c_void_p(field), ctypes.c_void_p(buffer.data_ptr()),
-                                  nx, nz, hx, sy, sz, j0, nrows, stream())
+        checked(lib.raw.sb200_unpack_rows(code, ctypes.c_void_p(field), ctypes.c_void_p(buffer.data_ptr()),
+                                          nx, nz, hx, sy, sz, j0, nrows, stream()), "sb200_unpack_rows")
 
     return HaloExchange(dist, rank, world_size, ny, width, make_buffer, pack, unpack, group)
 

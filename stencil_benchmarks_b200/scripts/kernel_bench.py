@@ -78,6 +78,30 @@ def time_loop(lib, enqueue, steps, warmup=5):
     return elapsed.value / steps
 
 
+def environment_settings(spec):
+    """'A=1,B=2;A=0' -> [{'A': '1', 'B': '2'}, {'A': '0'}]"""
+    settings = []
+    for group in (spec.split(";") if spec else []):
+        settings.append(dict(item.split("=", 1) for item in group.split(",") if item))
+    return settings
+
+
+class environment:
+    def __init__(self, values):
+        self.values = values
+
+    def __enter__(self):
+        self.saved = {k: os.environ.get(k) for k in self.values}
+        os.environ.update(self.values)
+
+    def __exit__(self, *exc):
+        for key, value in self.saved.items():
+            if value is None:
+                os.environ.pop(key, None)
+            else:
+                os.environ[key] = value
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--hdiff-sweep", default=None,
@@ -168,6 +192,12 @@ def main():
                                          1, 0, capi.VADV_AUTO, 0, t, None), args.repeat)
             report("vadv_1024x1024x160", dtype, nbytes, med, mn,
                    sbench_gbs=10 * int(np.prod(domain)) * size / med / 1e9)
+            for setting in environment_settings(args.vadv_sweep):
+                with environment(setting):
+                    med, mn = time_call(
+                        lambda t: lib.sb200_vadv(code, *[_vp(x.interior) for x in f], None, *domain, 1, sy, sz,
+                                                 1, 0, capi.VADV_AUTO, 0, t, None), args.repeat)
+                report(f"vadv {setting}", dtype, nbytes, med, mn)
             del f
         if "vadv3" in what:
             # all_components: u, v, w in one sweep sharing wcon (16 fields' worth of traffic)
@@ -186,6 +216,14 @@ def main():
                     code, 3, table(0), table(1), table(2), table(3), three(1, 0, 0), three(0, 1, 0),
                     _vp(wcon.interior), None, None, *domain, 1, sy, sz, capi.VADV_AUTO, 0, t, None), args.repeat)
             report("vadv_uvw_merged_1024x1024x160", dtype, nbytes, med, mn)
+            for setting in environment_settings(args.vadv_sweep):
+                with environment(setting):
+                    med, mn = time_call(
+                        lambda t: lib.sb200_vadv_components(
+                            code, 3, table(0), table(1), table(2), table(3), three(1, 0, 0), three(0, 1, 0),
+                            _vp(wcon.interior), None, None, *domain, 1, sy, sz, capi.VADV_AUTO, 0, t, None),
+                        args.repeat)
+                report(f"vadv_uvw {setting}", dtype, nbytes, med, mn)
             total_med = 0.0
             for c, (i, j) in enumerate([(1, 0), (0, 1), (0, 0)]):
                 med, mn = time_call(
