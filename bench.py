@@ -933,6 +933,17 @@ def extra_kernels(lib, capi, primary, reduce_max, world, peak, repeat=9):
         # scalar 1e-3 keeps the values finite over repeated triads
         record(f"stream_{name}_2^30_f64", factor * 8 * n,
                lambda t, op=op: lib.sb200_stream_op(op, capi.F64, *ptrs, n, 1e-3, 0, t, None))
+    # ... and the size sweep of configs[1] (triad, this rank's GPU; small sizes live in the L2)
+    sweep = {}
+    elapsed = ctypes.c_double()
+    for log2n in range(20, 30, 2):
+        times = []
+        for _ in range(repeat):
+            lib.sb200_stream_op(capi.STREAM_TRIAD, capi.F64, *ptrs, 1 << log2n, 1e-3, 0, ctypes.byref(elapsed), None)
+            times.append(elapsed.value)
+        sweep[f"2^{log2n}"] = round(3 * 8 * (1 << log2n) / statistics.median(times[1:]) / 1e9, 1)
+    sweep["2^30"] = round(result["stream_triad_2^30_f64"]["gbs_per_gpu"], 1)
+    result["stream_triad_size_sweep_f64_gbs"] = sweep
     del buffers
 
     # basic stencils 1024x1024x80 (configs[2]), float32 and float64
