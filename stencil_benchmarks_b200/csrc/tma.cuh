@@ -141,27 +141,5 @@ __device__ __forceinline__ void load_3d(void* dst, const CUtensorMap* map, int c
       : "memory");
 }
 
-// L2 eviction-priority policies for TMA loads (createpolicy): data that is read exactly once
-// should leave the L2 first, lines another CTA will read again should stay.
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  return policy;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-  return policy;
-}
-
-__device__ __forceinline__ void load_3d_hint(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                             uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-      "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-      : "memory");
-}
-
 }  // namespace tma
 }  // namespace sb200
