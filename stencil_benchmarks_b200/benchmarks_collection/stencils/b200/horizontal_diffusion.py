@@ -5,6 +5,7 @@ stencil_benchmarks/benchmarks_collection/stencils/cuda_hip/horizontal_diffusion.
 """
 
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -159,6 +160,7 @@ class Partitioned(HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
                 event = _vp()
                 lib.sb200_event_create(ctypes.byref(event))
                 slab["events"].append(event)
+                weakref.finalize(self, lib.raw.sb200_event_destroy, event)
             slabs.append(slab)
         for a, b in zip(slabs, slabs[1:]):
             lib.sb200_enable_peer_access(a["device"], b["device"])

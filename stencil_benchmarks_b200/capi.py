@@ -164,7 +164,11 @@ def jit_library(compiler, compiler_flags, source):
         except FileNotFoundError as error:
             raise cabi.CompilationError(f"compiler not found: {compiler}") from error
     else:
+        import atexit
+        import shutil
+
         directory = pathlib.Path(tempfile.mkdtemp(prefix="sb200_jit_"))
+        atexit.register(shutil.rmtree, directory, ignore_errors=True)  # the loaded .so stays mapped
         (directory / "source.cu").write_text(code)
         try:
             library = cabi.compile_library([directory / "source.cu"], directory / "library.so", command)

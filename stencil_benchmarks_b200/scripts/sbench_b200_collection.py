@@ -47,6 +47,11 @@ FAMILIES = {
     "vertical-advection-bandwidth": (160, {}, [
         ("thomas-onchip", vadv.Thomas, dict(coefficients="auto")),
         ("thomas-global", vadv.Thomas, dict(coefficients="global")),
+        ("thomas-uvw", vadv.Thomas, dict(coefficients="auto", all_components=True)),
+    ]),
+    # one domain partitioned over 1, 2, 4, 8 GPUs of the box (as many as it has): strong scaling
+    "horizontal-diffusion-multi-gpu": (80, {}, [
+        (f"partitioned-{gpus}", hdiff.Partitioned, dict(gpus=gpus)) for gpus in (1, 2, 4, 8)
     ]),
 }
 
@@ -64,9 +69,12 @@ def _family_command(family):
     @click.option("--executions", "-e", type=int, default=101)
     @click.option("--option", "-o", multiple=True)
     def command(output, executions, option):
+        from stencil_benchmarks_b200 import capi
+
         kwargs = common(option, **extra)
         configurations = [Configuration(cls, name=name, **cls_kwargs, **kwargs)
-                          for name, cls, cls_kwargs in members]
+                          for name, cls, cls_kwargs in members
+                          if cls_kwargs.get("gpus", 1) <= max(capi.device_count(), 1)]
         run_scaling_benchmark(configurations, executions, domain_range=domains(levels)).to_csv(output)
 
     return command
