@@ -9,7 +9,9 @@
 //
 // Variant ONCHIP (fast path, see the block comment above vadv_onchip_kernel): the eliminated
 // coefficients never leave the SM -- c lives in tensor memory (TMEM), the folded right-hand side
-// in shared memory -- so HBM traffic is the algorithmic minimum of 5 reads + 1 write.
+// in shared memory -- so HBM traffic is the algorithmic minimum of 5 reads + 1 write.  One launch
+// solves one component (u) or all three (u, v, w: the reference's merged kernel,
+// templates/vertical_advection_localmemmerged.j2:392-462), which then share wcon through the L2.
 //
 // Variant GLOBAL ("classic" data flow): one thread per (i, j) column,
 // consecutive lanes on consecutive i so every level is one coalesced row
@@ -126,6 +128,8 @@ __global__ void __launch_bounds__(128)
 // ---------------------------------------------------------------------------------
 // Persistent CTAs (one per SM): 4 compute warps (float32: 8) + 1 TMA producer warp.  A batch is
 // 128 (float32: 256) consecutive-i columns of one j row; thread t owns column i_t + t for all levels.
+// Work items (batch, component) are drawn from a global counter by the producer lane (see the
+// comment above the kernel): SMs do not progress at the same speed, static round robin is 6 % slower.
 //
 //  * Input levels arrive through a TMA ring (boxes of one batch x KD levels for ustage, upos,
 //    utens, utensstage and wcon; the wcon tile carries 16 more bytes per level so that wcon(i+1)
