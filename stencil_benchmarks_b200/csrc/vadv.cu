@@ -731,11 +731,10 @@ struct VadvSystem {
   int ishift, jshift;
 };
 
-template <class T>
-int launch_vadv_onchip(const VadvSystem<T>* systems, int ncomp, const T* wcon, int64_t nx, int64_t ny,
-                       int64_t nz, int64_t sy, int64_t sz, int dry_runs, double* time, cudaStream_t stream,
-                       bool* used) {
-  constexpr int KD = 4;
+template <class T, int KD>
+int launch_vadv_onchip_kd(const VadvSystem<T>* systems, int ncomp, const T* wcon, int64_t nx, int64_t ny,
+                          int64_t nz, int64_t sy, int64_t sz, int dry_runs, double* time, cudaStream_t stream,
+                          bool* used) {
   constexpr int COLS = vcfg::cols<T>();
   *used = false;
   // TMEM: c of every slot, plus e of as many slots as the thread's remaining columns hold
@@ -818,6 +817,24 @@ int launch_vadv_onchip(const VadvSystem<T>* systems, int ncomp, const T* wcon, i
   const int rc = timed(launch, dry_runs, time, stream);
   if (!counter_ok) return fail("sb200_vadv: cannot allocate or reset the work counter");
   return rc;
+}
+
+// Levels per ring stage: 4 for float64, 8 for float32 (SB200_VADV_KD overrides, a tuning aid).
+// A stage costs a fixed ~40 instructions per warp (barrier wait, release, slot bookkeeping, the
+// renormalisation of the forward triple); the float32 kernel -- two warps per scheduler, issue
+// bound -- gains 10 % from paying them half as often (0.625 against 0.696 ms, u/v/w 1.72 against
+// 2.02 ms), the float64 kernel, which waits for HBM as often as for its own instructions, gains
+// nothing (1.200 against 1.202 ms) and would give up four of its seven stages of prefetch depth
+// (profiles/vadv_kd8_r02.log).
+template <class T>
+int launch_vadv_onchip(const VadvSystem<T>* systems, int ncomp, const T* wcon, int64_t nx, int64_t ny,
+                       int64_t nz, int64_t sy, int64_t sz, int dry_runs, double* time, cudaStream_t stream,
+                       bool* used) {
+  int kd = sizeof(T) == 4 ? 8 : 4;
+  if (const char* env = std::getenv("SB200_VADV_KD")) kd = std::atoi(env);
+  if (kd == 8)
+    return launch_vadv_onchip_kd<T, 8>(systems, ncomp, wcon, nx, ny, nz, sy, sz, dry_runs, time, stream, used);
+  return launch_vadv_onchip_kd<T, 4>(systems, ncomp, wcon, nx, ny, nz, sy, sz, dry_runs, time, stream, used);
 }
 
 template <class T>
