@@ -70,14 +70,16 @@ class HaloExchange:
 
     def __init__(self, dist, rank: int, world_size: int, ny: int, width: int,
                  make_buffer: Callable, pack: Callable, unpack: Callable, group=None):
-        if width > ny:
-            raise ValueError("halo wider than the local slab")
+        counts = [int(ny)]
         if world_size > 1:
-            # the neighbours send `width` rows of THEIR slabs: every slab must hold that many
+            # the neighbours send `width` rows of THEIR slabs: every slab must hold that many.  All
+            # ranks take part in the gather before anybody raises, so that all of them refuse together
             counts = [None] * world_size
             dist.all_gather_object(counts, int(ny), group=group)
-            if min(counts) < width:
-                raise ValueError(f"halo of width {width} wider than the smallest slab ({min(counts)} rows)")
+        if width > ny:
+            raise ValueError("halo wider than the local slab")
+        if min(counts) < width:
+            raise ValueError(f"halo of width {width} wider than the smallest slab ({min(counts)} rows)")
         self.dist = dist
         self.rank, self.world_size = rank, world_size
         self.ny, self.width = ny, width

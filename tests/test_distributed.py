@@ -111,3 +111,28 @@ def test_halo_exchange_gloo(world, width):
         assert ok_result, f"rank {rank}: partitioned hdiff differs from the global result"
         faces = (rank > 0) + (rank < world - 1)
         assert nbytes == faces * width * (shape[0] + 2 * halo[0]) * (shape[2] + 2 * halo[2]) * 8
+
+
+def _narrow_worker(rank, world, port, results):
+    """Unequal slabs where ONE rank holds fewer rows than the halo is wide: every rank must refuse
+    (the neighbours would receive rows the narrow slab does not have)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ny = 2 if rank == 1 else 6
+        try:
+            distributed.HaloExchange(dist, rank, world, ny, 3, lambda n: torch.empty(n), None, None)
+        except ValueError as error:
+            results[rank] = str(error)
+        else:
+            results[rank] = "accepted"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_refuses_a_slab_narrower_than_the_halo():
+    results = mp.Manager().dict()
+    mp.spawn(_narrow_worker, args=(2, _free_port(), results), nprocs=2, join=True)
+    assert "wider than the local slab" in results[1]
+    assert "smallest slab (2 rows)" in results[0]
