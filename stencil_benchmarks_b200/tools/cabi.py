@@ -9,7 +9,7 @@ Mirrors ``stencil_benchmarks/tools/compilation.py`` of the reference (file kept 
   Python warning and the captured stdout is the return value (that is how
   STREAM hands back its table, stream/cuda_hip.py:121-144).
 * stdout/stderr are captured at file-descriptor level (compilation.py:54-86) so
-  output written by C code is seen.
+  output written by C code is seen (``FdCapture``).
 * ``dtype_cname`` / ``data_ptr`` (compilation.py:254-282) keep their meaning.
 
 Unlike ``GnuLibrary`` the library is pre-built in-tree by ``__graft_entry__.build()``
@@ -19,13 +19,13 @@ reference-style "compile this source now" path for out-of-tree use.
 
 import contextlib
 import ctypes
-import io
 import os
 import pathlib
 import subprocess
+import sys
 import tempfile
 import warnings
-from typing import Iterator, List, Optional, TextIO, Tuple, Union
+from typing import List, Optional, Tuple, Union
 
 import numpy as np
 
@@ -38,27 +38,71 @@ class ExecutionError(RuntimeError):
     pass
 
 
-@contextlib.contextmanager
-def _redirect_fd(fileno: int, target: TextIO) -> Iterator[None]:
-    saved = os.dup(fileno)
-    try:
-        with tempfile.TemporaryFile() as capture:
-            os.dup2(capture.fileno(), fileno)
-            try:
-                yield
-            finally:
-                os.dup2(saved, fileno)
-                capture.seek(0)
-                target.write(capture.read().decode(errors="replace"))
-    finally:
-        os.close(saved)
+class FdCapture:
+    """What C code writes to file descriptors 1 and 2 while the block runs.
+
+    The descriptors are pointed at two anonymous files for the duration of the block and restored
+    on every way out of it (Python-level redirection would not see ``printf`` / ``fprintf`` of a
+    shared library); afterwards ``out`` and ``err`` hold the text.  Python's own buffered streams
+    are flushed first so that nothing written earlier lands in the capture.
+    """
+
+    def __init__(self):
+        self.out = self.err = ""
+        self._slots = []
+
+    def __enter__(self):
+        for stream in (sys.stdout, sys.stderr):
+            with contextlib.suppress(Exception):
+                stream.flush()
+        try:
+            for fileno in (1, 2):
+                scratch = tempfile.TemporaryFile()
+                self._slots.append((fileno, os.dup(fileno), scratch))
+                os.dup2(scratch.fileno(), fileno)
+        except BaseException:
+            self._restore()
+            raise
+        return self
+
+    def _restore(self):
+        texts = {}
+        while self._slots:
+            fileno, original, scratch = self._slots.pop()
+            os.dup2(original, fileno)
+            os.close(original)
+            scratch.seek(0)
+            texts[fileno] = scratch.read().decode(errors="replace")
+            scratch.close()
+        return texts
+
+    def __exit__(self, *exc):
+        texts = self._restore()
+        self.out, self.err = texts.get(1, ""), texts.get(2, "")
+        return False
 
 
-@contextlib.contextmanager
-def capture_output(stdout: TextIO, stderr: TextIO) -> Iterator[None]:
-    """Capture what C code writes to file descriptors 1 and 2."""
-    with _redirect_fd(1, stdout), _redirect_fd(2, stderr):
-        yield
+class CFunction:
+    """One ``extern "C" int f(...)`` of a library under the reference's call convention
+    (compilation.py:155-196): the return value is a status, 0 = success; a failure raises
+    ``ExecutionError`` carrying what the function wrote to stderr; stderr text of a successful
+    call is a Python warning; the call evaluates to what the function wrote to stdout.  The
+    optional keyword ``argtypes`` sets the ctypes prototype, as the reference's callers do."""
+
+    def __init__(self, name: str, function):
+        self.__name__ = name
+        self._function = function
+
+    def __call__(self, *args, argtypes=None) -> str:
+        if argtypes is not None:
+            self._function.argtypes = argtypes
+        with FdCapture() as captured:
+            status = self._function(*args)
+        if status != 0:
+            raise ExecutionError(captured.err)
+        if captured.err:
+            warnings.warn(f"unexpected output in call to {self.__name__}(…) to stderr:\n" + captured.err)
+        return captured.out
 
 
 class Library:
@@ -79,26 +123,11 @@ class Library:
         """The bare ctypes handle (no output capture, no exception mapping)."""
         return self._library
 
-    def __getattr__(self, attr: str):
-        func = getattr(self._library, attr)
-
-        def wrapper(*args, argtypes=None):
-            if argtypes is not None:
-                func.argtypes = argtypes
-            stdout = io.StringIO()
-            stderr = io.StringIO()
-            with capture_output(stdout, stderr):
-                result = func(*args)
-            stdout = stdout.getvalue()
-            stderr = stderr.getvalue()
-            if result != 0:
-                raise ExecutionError(stderr)
-            if stderr:
-                warnings.warn(f"unexpected output in call to {attr}(…) to stderr:\n" + stderr)
-            return stdout
-
-        wrapper.__name__ = attr
-        return wrapper
+    def __getattr__(self, attr: str) -> CFunction:
+        # only reached for names that are not instance attributes: every other name is a symbol
+        if attr.startswith("_"):
+            raise AttributeError(attr)
+        return CFunction(attr, getattr(self._library, attr))
 
 
 def compile_library(

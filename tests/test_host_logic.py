@@ -306,3 +306,39 @@ def test_hdiff_tiling_covers_every_row_once(monkeypatch, dtype, domain, cfg):
     assert (rows == 1).all()
     if cfg is None:
         assert (j1 - j0).max() <= 32  # default segments (profiles/hdiff_segments_r01.log)
+
+
+def test_call_convention_of_a_loaded_library(tmp_path):
+    """The GnuLibrary convention (tools/compilation.py:155-196 of the reference, its doctest at
+    :104-116): stdout of the C function is the call's value, a non-zero status raises with the
+    stderr text, stderr text of a successful call is a warning, `argtypes=` sets the prototype;
+    the descriptors are back in place afterwards."""
+    import ctypes
+    import os
+    import warnings
+
+    source = tmp_path / "convention.c"
+    source.write_text(
+        '#include <stdio.h>\n'
+        'int hello(void) { printf("Hello world!"); fflush(stdout); return 0; }\n'
+        'int fails(int code) { fprintf(stderr, "reason %d", code); fflush(stderr); return code; }\n'
+        'int chatty(void) { fprintf(stderr, "note"); fflush(stderr); printf("data"); fflush(stdout); return 0; }\n'
+        'int scaled(double x) { printf("%.1f", 2 * x); fflush(stdout); return 0; }\n')
+    before = (os.fstat(1).st_ino, os.fstat(2).st_ino)
+    lib = cabi.compile_library([source], tmp_path / "convention.so", ["gcc", "-O1"])
+    assert lib.hello() == "Hello world!"
+    assert lib.hello.__name__ == "hello"
+    with pytest.raises(cabi.ExecutionError, match="reason 3"):
+        lib.fails(ctypes.c_int(3))
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        assert lib.chatty() == "data"
+    assert any("chatty" in str(w.message) and "note" in str(w.message) for w in caught)
+    assert lib.scaled(1.25, argtypes=[ctypes.c_double]) == "2.5"
+    with pytest.raises(AttributeError):
+        lib.no_such_function
+    assert (os.fstat(1).st_ino, os.fstat(2).st_ino) == before
+    with pytest.raises(cabi.CompilationError):
+        bad = tmp_path / "bad.c"
+        bad.write_text("int broken( { return 0; }\n")
+        cabi.compile_library([bad], tmp_path / "bad.so", ["gcc"])
