@@ -32,7 +32,9 @@ Keys beyond the base contract:
                     copy/scale/add/triad at 2^30 float64, basic copy / Laplacian (float32 + float64),
                     vertical advection 1024x1024x160 (u, and u/v/w in one sweep), each with its
                     fraction of the measured and of the nominal peak
-  cpu_baseline      the reference's OpenMP kernels (oracle/_ref) on this box's cores (N = 1 only)
+  cpu_baseline      the reference's OpenMP kernels (oracle/_ref) on this box's cores (N = 1 only);
+                    `also`: the other BASELINE configs on the host cores (hdiff 128x128x80, basic copy /
+                    Laplacian 1024x1024x80, vadv 1024x1024x160), best OpenMP variant each
   reference_gpu     the reference's own CUDA kernels recompiled for sm_100 (best of the block-size
                     sweep in oracle/_ref), same box, same run (N = 1 only)
 """
@@ -261,6 +263,66 @@ def time_reference(workload, steps, warmup, budget_s=None):
     return best
 
 
+# the other BASELINE.json configs on the host cores ("CPU OpenMP numbers alongside"):
+# (label, kernels of oracle/_ref to try, workload whose byte formula applies, domain)
+CPU_OTHER_CONFIGS = [
+    ("hdiff_128x128x80_f64 (BASELINE configs[0], cache resident)",
+     ["hdiff_otf_128x128x80_f64", "hdiff_otfvec_128x128x80_f64", "hdiff_rolling_128x128x80_f64"],
+     "hdiff", (128, 128, 80)),
+    ("basic_copy_1024x1024x80_f64", ["copy_1dvec_1024x1024x80_f64"], "basic", (1024, 1024, 80)),
+    ("basic_laplacian_ij_1024x1024x80_f64", ["laplacian_3dvec_1024x1024x80_f64"], "basic", (1024, 1024, 80)),
+    ("vadv_1024x1024x160_f64", ["vadv_kmiddlevec_1024x1024x160_f64", "vadv_kinnermostvec_1024x1024x160_f64"],
+     "vadv", (1024, 1024, 160)),
+    ("hdiff_2048x2048x80_f64", WORKLOADS["hdiff"]["reference_kernels"][2:], "hdiff", (2048, 2048, 80)),
+]
+
+
+def cpu_other_configs(primary, budget_s=20.0):
+    """The reference's OpenMP kernels of the BASELINE configs other than `primary`, on all host
+    cores: per config the best variant's mean sweep time and ALGORITHMIC GB/s (the byte formulas of
+    `algorithmic_bytes`, basic: 2*N*s).  Bounded: every variant gets an equal share of `budget_s`,
+    at least one warm and one timed sweep."""
+    from oracle import ref_cpu
+
+    if not ref_cpu.available():
+        return {"unavailable": "oracle/_ref is not built"}
+    ref_cpu.use_all_cores()
+    present = ref_cpu.manifest()
+    configs = [(label, [k for k in kernels if k in present], workload, domain)
+               for label, kernels, workload, domain in CPU_OTHER_CONFIGS
+               if workload == "basic" or workload != primary or domain != tuple(WORKLOADS[primary]["domain"])]
+    variants = sum(len(kernels) for _, kernels, _, _ in configs)
+    result = {}
+    for label, kernels, workload, domain in configs:
+        best = None
+        for name in kernels:
+            share = budget_s / max(variants, 1)
+            try:
+                kernel = ref_cpu.Kernel(name)
+                fields = kernel.fields(seed=0, fast=True)
+                kernel(fields)
+                times = []
+                start = time.perf_counter()
+                while not times or (time.perf_counter() - start < share and len(times) < 50):
+                    times.append(kernel(fields))
+                mean = sum(times) / len(times)
+                if best is None or mean < best[1]:
+                    best = (name, mean, len(times), kernel.isa)
+                del fields, kernel
+            except Exception as error:  # noqa: BLE001 - one variant must not lose the others
+                result.setdefault("failed", []).append(f"{name}: {error}")
+        if best is None:
+            continue
+        if workload == "basic":
+            nbytes = 2 * domain[0] * domain[1] * domain[2] * 8
+        else:
+            nbytes = algorithmic_bytes(workload, domain)
+        result[label] = {"kernel": best[0], "ms": best[1] * 1e3, "gbs": nbytes / best[1] / 1e9,
+                         "sweeps": best[2], "march": best[3], "variants_tried": len(kernels)}
+    result["cores"] = ref_cpu.threads()
+    return result
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -287,6 +349,8 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "one host sweeps ONE BASELINE domain whatever --gpus says: at N > 1 the GPU arm sweeps N of them",
     }
+    if not args.no_extras:
+        line["also"] = cpu_other_configs(args.workload)
     print(json.dumps(line), flush=True)
     return 0
 
@@ -762,6 +826,10 @@ def run_b200(args):
         except Exception as error:  # the baseline must not lose the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count(),
                                     "kind": "reference", "sample": f"failed: {error}"}
+        try:
+            line["cpu_baseline"]["also"] = cpu_other_configs(args.workload, budget_s=12.0)
+        except Exception as error:  # noqa: BLE001
+            line["cpu_baseline"]["also"] = {"unavailable": f"{type(error).__name__}: {error}"}
         line["reference_gpu"] = reference_gpu(args.workload, ms_per_step)
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -48,3 +48,22 @@ def test_manifest_describes_baseline_configs():
     assert entries["hdiff_otf_128x128x80_f64"]["domain"] == [128, 128, 80]
     assert entries["hdiff_otf_128x128x80_f64"]["data_size"] == 32680448
     assert "hdiff_otfvec_2048x2048x80_f64" in entries and "vadv_kmiddlevec_1024x1024x160_f64" in entries
+
+
+def test_bench_times_the_other_configs_on_the_host(monkeypatch):
+    """bench.py's `cpu_baseline.also`: best OpenMP variant per config with algorithmic bytes;
+    the primary workload's own config is left to `cpu_baseline.value`, a missing kernel is skipped."""
+    import bench
+
+    monkeypatch.setattr(bench, "CPU_OTHER_CONFIGS", [
+        bench.CPU_OTHER_CONFIGS[0],
+        ("hdiff_2048x2048x80_f64", ["hdiff_rolling_2048x2048x80_f64"], "hdiff", (2048, 2048, 80)),
+        ("not built", ["no_such_kernel"], "vadv", (8, 8, 8)),
+    ])
+    result = bench.cpu_other_configs("hdiff", budget_s=0.5)
+    label = bench.CPU_OTHER_CONFIGS[0][0]
+    assert set(result) == {label, "cores"}
+    entry = result[label]
+    assert entry["variants_tried"] == 3 and entry["sweeps"] >= 1 and entry["ms"] > 0
+    nbytes = (2 * 128 * 128 * 80 + 132 * 132 * 80) * 8
+    assert entry["gbs"] == pytest.approx(nbytes / (entry["ms"] * 1e-3) / 1e9)
