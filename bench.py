@@ -295,11 +295,17 @@ def cpu_other_configs(primary, budget_s=20.0):
     result = {}
     for label, kernels, workload, domain in configs:
         best = None
+        fields = layout = None
         for name in kernels:
             share = budget_s / max(variants, 1)
             try:
                 kernel = ref_cpu.Kernel(name)
-                fields = kernel.fields(seed=0, fast=True)
+                # variants rendered for the same layout sweep the same fields (generating 11 GB of
+                # vadv fields takes longer than timing them)
+                wanted = tuple(kernel.entry[key] for key in ("strides", "alignment", "dtype", "args"))
+                if fields is None or wanted != layout:
+                    fields = None
+                    fields, layout = kernel.fields(seed=0, fast=True), wanted
                 kernel(fields)
                 times = []
                 start = time.perf_counter()
@@ -308,9 +314,10 @@ def cpu_other_configs(primary, budget_s=20.0):
                 mean = sum(times) / len(times)
                 if best is None or mean < best[1]:
                     best = (name, mean, len(times), kernel.isa)
-                del fields, kernel
+                del kernel
             except Exception as error:  # noqa: BLE001 - one variant must not lose the others
                 result.setdefault("failed", []).append(f"{name}: {error}")
+        del fields
         if best is None:
             continue
         if workload == "basic":
