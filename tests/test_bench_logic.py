@@ -67,3 +67,23 @@ def test_edge_parity_detects_a_wrong_halo_row():
     native.hdiff(stale, fields["coeff"], out, halo)
     result = bench.edge_parity(Slab, out, start, "test")
     assert not result["ok"] and result["max_abs_err"] > 1e-6
+
+
+def test_reference_arm_falls_back_to_the_oracle_port(monkeypatch, capsys):
+    """Without oracle/_ref (a tree built where the reference was absent) `--impl reference` still
+    prints a line: the C restatement on the host cores, kind "port"."""
+    import argparse
+    import json
+
+    from oracle import ref_cpu
+
+    monkeypatch.setattr(ref_cpu, "available", lambda: False)
+    monkeypatch.setitem(bench.WORKLOADS, "hdiff", dict(bench.WORKLOADS["hdiff"], domain=(64, 48, 5)))
+    monkeypatch.setitem(bench.WORKLOADS, "vadv", dict(bench.WORKLOADS["vadv"], domain=(32, 16, 12)))
+    for workload in ("hdiff", "vadv"):
+        args = argparse.Namespace(workload=workload, steps=2, warmup=1, gpus=1, no_extras=False)
+        assert bench.run_reference(args) == 0
+        line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
+        assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+        assert line["also"] == {"unavailable": "oracle/_ref is not built"}
