@@ -80,10 +80,13 @@ def test_reference_arm_falls_back_to_the_oracle_port(monkeypatch, capsys):
     monkeypatch.setattr(ref_cpu, "available", lambda: False)
     monkeypatch.setitem(bench.WORKLOADS, "hdiff", dict(bench.WORKLOADS["hdiff"], domain=(64, 48, 5)))
     monkeypatch.setitem(bench.WORKLOADS, "vadv", dict(bench.WORKLOADS["vadv"], domain=(32, 16, 12)))
-    for workload in ("hdiff", "vadv"):
-        args = argparse.Namespace(workload=workload, steps=2, warmup=1, gpus=1, no_extras=False)
+    for workload, gpus in (("hdiff", 2), ("vadv", 1)):
+        args = argparse.Namespace(workload=workload, steps=2, warmup=1, gpus=gpus, no_extras=False)
         assert bench.run_reference(args) == 0
         line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+        # both arms of the driver's comparison carry the same config at every N
+        assert line["config"] == bench.workload_config(workload, gpus, "peer", "weak", False)
+        assert line["n_gpus"] == gpus and ("J slabs" in line["cpu_baseline"]["sample"]) == (gpus > 1)
         assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
         assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
         assert line["also"] == {"unavailable": "oracle/_ref is not built"}
