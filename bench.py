@@ -52,6 +52,7 @@ import time
 
 ROOT = pathlib.Path(__file__).parent.resolve()
 sys.path.insert(0, str(ROOT))
+PROCESS_START = time.perf_counter()
 
 WORKLOADS = {
     "hdiff": dict(domain=(2048, 2048, 80), dtype="float64", halo=(3, 3, 3),
@@ -874,28 +875,43 @@ def run_b200(args):
     if not args.no_extras:
         line["also"] = extra_kernels(lib, capi, args.workload, reduce_max, world, peak)
     if rank == 0 and world == 1 and not args.no_extras and not args.no_cpu_baseline:
-        try:
-            best = time_reference(args.workload, steps=5, warmup=1, budget_s=24.0)
-            line["cpu_baseline"] = {
-                "value": nbytes / best["mean_s"] / 1e9, "unit": "GB/s", "cores": best["threads"],
-                "kind": best.get("kind", "reference"),
-                "sample": f"{best['sweeps']} full sweeps, "
-                          + ("reference OpenMP kernel" if best.get("kind", "reference") == "reference" else "kernel")
-                          + f" {best['name']} (-march={best['isa']}), best of: {', '.join(best['tried'])}"}
-        except Exception as error:  # the baseline must not lose the GPU numbers
-            line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count(),
-                                    "kind": "reference", "sample": f"failed: {error}"}
-        try:
-            line["cpu_baseline"]["also"] = cpu_other_configs(args.workload, budget_s=12.0)
-        except Exception as error:  # noqa: BLE001
-            line["cpu_baseline"]["also"] = {"unavailable": f"{type(error).__name__}: {error}"}
-        line["reference_gpu"] = reference_gpu(args.workload, ms_per_step)
+        line.update(baselines_beside(args, nbytes, ms_per_step))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def baselines_beside(args, nbytes, ms_per_step):
+    """The keys of the N = 1 line that are measured beside the GPU numbers, after them: `cpu_baseline`
+    (the reference's OpenMP kernels on the host cores, bounded sample; contract), and the two
+    optional comparisons `cpu_baseline.also` and `reference_gpu`, which are skipped -- and say so --
+    once the process has used its wall-clock allowance.  Nothing here may lose the GPU numbers."""
+    keys = {}
+    try:
+        best = time_reference(args.workload, steps=5, warmup=1, budget_s=24.0)
+        kind = best.get("kind", "reference")
+        keys["cpu_baseline"] = {
+            "value": nbytes / best["mean_s"] / 1e9, "unit": "GB/s", "cores": best["threads"], "kind": kind,
+            "sample": f"{best['sweeps']} full sweeps, " + ("reference OpenMP kernel" if kind == "reference" else "kernel")
+                      + f" {best['name']} (-march={best['isa']}), best of: {', '.join(best['tried'])}"}
+    except Exception as error:  # noqa: BLE001
+        keys["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count(),
+                                "kind": "reference", "sample": f"failed: {error}"}
+
+    def within_allowance():
+        return time.perf_counter() - PROCESS_START < args.optional_until_s
+
+    skipped = {"unavailable": f"skipped: the run was past --optional-until-s {args.optional_until_s:.0f} s"}
+    try:
+        keys["cpu_baseline"]["also"] = (cpu_other_configs(args.workload, budget_s=12.0)
+                                        if within_allowance() else skipped)
+    except Exception as error:  # noqa: BLE001
+        keys["cpu_baseline"]["also"] = {"unavailable": f"{type(error).__name__}: {error}"}
+    keys["reference_gpu"] = reference_gpu(args.workload, ms_per_step) if within_allowance() else skipped
+    return keys
 
 
 def reference_gpu(workload, ours_ms):
@@ -1147,6 +1163,9 @@ def main():
     parser.add_argument("--e2e-chunks", type=int, default=8)
     parser.add_argument("--no-extras", action="store_true")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--optional-until-s", type=float, default=300.0,
+                        help="wall-clock seconds after which the optional comparisons of the N=1 line "
+                             "(cpu_baseline.also, reference_gpu) are skipped")
     args = parser.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -90,3 +90,34 @@ def test_reference_arm_falls_back_to_the_oracle_port(monkeypatch, capsys):
         assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
         assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
         assert line["also"] == {"unavailable": "oracle/_ref is not built"}
+
+
+def test_baselines_beside_the_gpu_numbers(monkeypatch):
+    """cpu_baseline is always there; the optional comparisons run inside the wall-clock allowance
+    only, and a failing baseline does not raise."""
+    import argparse
+
+    fake = dict(name="k", isa="native", mean_s=0.05, sweeps=5, threads=16, tried=["k 50.0 ms"])
+    monkeypatch.setattr(bench, "time_reference", lambda *a, **k: dict(fake))
+    monkeypatch.setattr(bench, "cpu_other_configs", lambda *a, **k: {"x": 1})
+    monkeypatch.setattr(bench, "reference_gpu", lambda workload, ms: {"ms": 2 * ms})
+    args = argparse.Namespace(workload="hdiff", optional_until_s=1e9)
+    keys = bench.baselines_beside(args, 8_000_000_000, 1.25)
+    assert keys["cpu_baseline"]["value"] == pytest.approx(160.0) and keys["cpu_baseline"]["cores"] == 16
+    assert keys["cpu_baseline"]["kind"] == "reference" and "reference OpenMP kernel k" in keys["cpu_baseline"]["sample"]
+    assert keys["cpu_baseline"]["also"] == {"x": 1} and keys["reference_gpu"] == {"ms": 2.5}
+
+    args.optional_until_s = 0.0
+    keys = bench.baselines_beside(args, 8_000_000_000, 1.25)
+    assert keys["cpu_baseline"]["value"] == pytest.approx(160.0)
+    assert "skipped" in keys["cpu_baseline"]["also"]["unavailable"] and "skipped" in keys["reference_gpu"]["unavailable"]
+
+    def broken(*a, **k):
+        raise RuntimeError("no compiler")
+
+    monkeypatch.setattr(bench, "time_reference", broken)
+    monkeypatch.setattr(bench, "cpu_other_configs", broken)
+    args.optional_until_s = 1e9
+    keys = bench.baselines_beside(args, 8_000_000_000, 1.25)
+    assert keys["cpu_baseline"]["value"] is None and "no compiler" in keys["cpu_baseline"]["sample"]
+    assert "no compiler" in keys["cpu_baseline"]["also"]["unavailable"]
