@@ -342,3 +342,31 @@ def test_call_convention_of_a_loaded_library(tmp_path):
         bad = tmp_path / "bad.c"
         bad.write_text("int broken( { return 0; }\n")
         cabi.compile_library([bad], tmp_path / "bad.so", ["gcc"])
+
+
+def test_ctypes_prototypes_match_the_header_parameter_by_parameter():
+    """A ctypes prototype that drifts from include/sbench_b200.h (a missing argument, an int where
+    the header says int64_t) corrupts the call on the GPU box only: compare them here."""
+    import re
+
+    text = capi.HEADER_PATH.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    declarations = re.findall(r"\b(int|uint64_t)\s+(sb200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert {name for _, name, _ in declarations} == set(capi.PROTOTYPES)
+    scalars = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+               "size_t": ctypes.c_size_t, "double": ctypes.c_double, "uint32_t": ctypes.c_uint32,
+               "unsigned": ctypes.c_uint32, "unsigned int": ctypes.c_uint32}
+    for restype, name, parameters in declarations:
+        expected_restype, argtypes = capi.PROTOTYPES[name]
+        assert scalars[restype] is expected_restype, name
+        declared = [p.strip() for p in parameters.replace("\n", " ").split(",")
+                    if p.strip() and p.strip() != "void"]
+        assert len(declared) == len(argtypes), f"{name}: {len(declared)} parameters declared, {len(argtypes)} bound"
+        for position, (parameter, bound) in enumerate(zip(declared, argtypes)):
+            where = f"{name} argument {position} ({parameter})"
+            if "*" in parameter:
+                assert bound in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(bound, ctypes._Pointer), where
+                continue
+            ctype = re.sub(r"\bconst\b", "", parameter).strip().rsplit(" ", 1)[0].strip()
+            assert scalars[ctype] is bound, where
