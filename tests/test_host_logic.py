@@ -370,3 +370,35 @@ def test_ctypes_prototypes_match_the_header_parameter_by_parameter():
                 continue
             ctype = re.sub(r"\bconst\b", "", parameter).strip().rsplit(" ", 1)[0].strip()
             assert scalars[ctype] is bound, where
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 and a C program must link
+    against the library and call it (entry points that need no GPU: version, launch counter, the
+    host-side tiling query, an argument error with its stderr reason)."""
+    header_dir = capi.HEADER_PATH.parent
+    for compiler, language, standard in (("gcc", "c", "-std=c99"), ("g++", "c++", "-std=c++11")):
+        check = subprocess.run([compiler, standard, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", language,
+                                str(capi.HEADER_PATH)], capture_output=True, text=True)
+        assert check.returncode == 0 and not check.stderr, check.stderr
+    source = tmp_path / "client.c"
+    source.write_text(
+        '#include <stdio.h>\n#include "sbench_b200.h"\n'
+        "int main(void) {\n"
+        "  int rows = 0, segments = 0, xtiles = 0; int64_t ctas = 0;\n"
+        "  if (sb200_version() < 100) return 2;\n"
+        "  if (sb200_launch_count() != 0) return 3;\n"
+        "  if (sb200_hdiff_tiling(SB200_F64, 2048, 2048, 80, &xtiles, &segments, &rows, &ctas) != 0) return 4;\n"
+        '  printf("%d %d %d %lld\\n", rows, segments, xtiles, (long long)ctas);\n'
+        "  return sb200_stream_configure(33, 0, 0, -1) != 0 ? 0 : 5;  /* rejected: not a multiple of 32 */\n"
+        "}\n")
+    binary = tmp_path / "client"
+    build = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", str(header_dir), str(source), "-o", str(binary),
+                            str(capi.LIBRARY_PATH), f"-Wl,-rpath,{capi.LIBRARY_PATH.parent}"],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(binary)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.returncode, run.stderr)
+    rows, segments, xtiles, ctas = (int(v) for v in run.stdout.split())
+    assert rows == 32 and segments == 64 and xtiles == 8 and ctas == 8 * 64 * 80
+    assert "multiple of 32" in run.stderr
