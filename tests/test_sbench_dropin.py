@@ -95,3 +95,37 @@ except compilation.ExecutionError as error:
                             timeout=300, cwd=str(tmp_path))
     assert result.returncode == 0, result.stderr
     assert "reference ExecutionError: sb200_hdiff: domain must be positive" in result.stdout
+
+
+def test_integration_stub_registers_in_the_reference(reference_path):
+    """The reference-side binding printed in INTEGRATION.md §2 is real code: executed as a module
+    of the reference's benchmark collection it registers in the CLI tree, loads the library at
+    setup(), resolves every prototype it sets, and maps a missing library to ParameterError."""
+    text = (ROOT / "INTEGRATION.md").read_text()
+    start = text.index("```python\n# b200/mixin.py") + len("```python\n")
+    stub = text[start:text.index("```", start)]
+    library = ROOT / "stencil_benchmarks_b200" / "csrc" / "libsbench_b200.so"
+    code = f"""
+import sys, types
+import stencil_benchmarks.benchmark as ref
+from stencil_benchmarks.cli import _cli_command
+name = "stencil_benchmarks.benchmarks_collection.stencils.b200.horizontal_diffusion"
+module = types.ModuleType(name)
+sys.modules[name] = module
+exec(compile({stub!r}, "INTEGRATION.md", "exec"), module.__dict__)
+assert module.Fused in ref.REGISTRY and module.StencilMixin not in ref.REGISTRY
+print(" ".join(_cli_command(module.Fused)))
+bench = module.Fused(domain=(16, 12, 5), library={str(library)!r}, verify=False)
+print(bench.strides, bench.lib.sb200_hdiff.argtypes is not None, bench.lib.sb200_version())
+try:
+    module.Fused(domain=(16, 12, 5), library="/nonexistent/libsbench_b200.so")
+except ref.ParameterError as error:
+    print("ParameterError")
+"""
+    result = run(code, reference_path)
+    assert result.returncode == 0, result.stderr
+    lines = result.stdout.strip().splitlines()
+    assert lines[0] == "stencils b200 horizontal_diffusion fused"
+    # alignment 128: rows of 16 + 2*3 doubles padded to 32; the library answers through the stub's handle
+    assert lines[1] == f"(1, 32, {32 * 18}) True 100"
+    assert lines[2] == "ParameterError"
