@@ -129,3 +129,30 @@ except ref.ParameterError as error:
     # alignment 128: rows of 16 + 2*3 doubles padded to 32; the library answers through the stub's handle
     assert lines[1] == f"(1, 32, {32 * 18}) True 100"
     assert lines[2] == "ParameterError"
+
+
+def test_committed_golden_vectors_are_what_the_reference_produces(reference_path):
+    """Provenance of tests/golden/*.npz: re-derive every case from the reference's own
+    verify_stencil (the committed generator, unmodified reference) and compare bit for bit."""
+    code = f"""
+import sys
+import numpy as np
+sys.path.insert(0, {str(ROOT / "tests" / "golden")!r})
+import make_golden as g
+checked = 0
+for seed, (name, stencil_class, kwargs, outputs) in enumerate(g.CASES):
+    bench = g.probe(stencil_class)(**kwargs)
+    data = g.seeded_fill(bench, 1000 + seed)
+    expected = g.capture_expected(bench, data)
+    stored = np.load(g.OUT / (name + ".npz"))
+    for field_name, field in zip(bench.args, data):
+        assert np.array_equal(stored["in_" + field_name], field), (name, field_name)
+    for output in outputs:
+        assert stored["expected_" + output].dtype == expected[output].dtype
+        assert np.array_equal(stored["expected_" + output], expected[output]), (name, output)
+    checked += 1
+print(checked)
+"""
+    result = run(code, reference_path)
+    assert result.returncode == 0, result.stderr
+    assert int(result.stdout.strip().splitlines()[-1]) == len(list((ROOT / "tests" / "golden").glob("*.npz"))) == 40
