@@ -156,3 +156,66 @@ print(checked)
     result = run(code, reference_path)
     assert result.returncode == 0, result.stderr
     assert int(result.stdout.strip().splitlines()[-1]) == len(list((ROOT / "tests" / "golden").glob("*.npz"))) == 40
+
+
+def test_oracle_equals_the_live_reference_on_random_cases(reference_path):
+    """Beyond the committed vectors: 48 random (stencil, domain, halo, dtype) cases, the expected
+    arrays captured from the reference's verify_stencil live, both oracle restatements bit for bit."""
+    code = f"""
+import sys
+import numpy as np
+sys.path.insert(0, {str(ROOT / "tests" / "golden")!r})
+sys.path.insert(0, {str(ROOT / "tests")!r})
+import make_golden as g
+import test_oracle as t
+from stencil_benchmarks.benchmarks_collection.stencils import base
+
+rng = np.random.default_rng(20261017)
+checked = 0
+for n in range(48):
+    kind = ["copy", "onesided", "symmetric", "laplacian", "hdiff", "vadv", "vadv_all"][n % 7]
+    dtype = ["float64", "float32"][(n // 7) % 2]
+    domain = tuple(int(v) for v in rng.integers(3, 22, 3))
+    halo = [int(v) for v in rng.integers(0, 4, 3)]
+    kwargs, outputs, name = dict(dtype=dtype, verify=True), ["out"], kind
+    if kind == "copy":
+        cls = base.CopyStencil
+    elif kind in ("onesided", "symmetric"):
+        axis = int(rng.integers(0, 3))
+        halo[axis] = max(halo[axis], 1)
+        cls = base.OnesidedAverageStencil if kind == "onesided" else base.SymmetricAverageStencil
+        kwargs["axis"], name = axis, f"{{kind}}_ax{{axis}}_x"
+    elif kind == "laplacian":
+        mask = int(rng.integers(1, 8))
+        halo = [max(h, 1) if mask >> a & 1 else h for a, h in enumerate(halo)]
+        cls = base.LaplacianStencil
+        kwargs.update(along_x=bool(mask & 1), along_y=bool(mask & 2), along_z=bool(mask & 4))
+        name = f"laplacian_m{{mask}}_x"
+    elif kind == "hdiff":
+        halo = [max(halo[0], 2), max(halo[1], 2), halo[2]]
+        cls = base.HorizontalDiffusionStencil
+    else:
+        cls = base.VerticalAdvectionStencil
+        domain = domain[:2] + (max(domain[2], 2),)
+        if kind == "vadv_all":
+            halo = [max(h, 1) for h in halo]
+            kwargs["all_components"] = True
+            outputs, name = ["utensstage", "vtensstage", "wtensstage"], "vadv_all_x"
+        else:
+            halo[0] = max(halo[0], 1)
+            outputs, name = ["utensstage"], "vadv_x"
+    bench = g.probe(cls)(domain=domain, halo=tuple(halo), **kwargs)
+    data = g.seeded_fill(bench, 5000 + n)
+    expected = g.capture_expected(bench, data)
+    case = {{"in_" + f: np.ascontiguousarray(v) for f, v in zip(bench.args, data)}}
+    case["halo"], case["domain"] = np.array(bench.halo), np.array(bench.domain)
+    for restatement in (t.expected_numpy, t.expected_c):
+        got = restatement(name, dict(case))
+        for output in outputs:
+            assert np.array_equal(got[output], expected[output]), (n, kind, dtype, domain, halo, restatement.__name__)
+    checked += 1
+print(checked)
+"""
+    result = run(code, reference_path)
+    assert result.returncode == 0, result.stderr[-3000:]
+    assert int(result.stdout.strip().splitlines()[-1]) == 48
