@@ -144,7 +144,6 @@ def jit_library(compiler, compiler_flags, source):
     mirror in tools/cabi.py does the same.  One compilation per (compiler, flags, source) and process.
     """
     import shlex
-    import tempfile
 
     key = (compiler, compiler_flags, source)
     if key in _JIT_CACHE:
@@ -164,14 +163,8 @@ def jit_library(compiler, compiler_flags, source):
         except FileNotFoundError as error:
             raise cabi.CompilationError(f"compiler not found: {compiler}") from error
     else:
-        import atexit
-        import shutil
-
-        directory = pathlib.Path(tempfile.mkdtemp(prefix="sb200_jit_"))
-        atexit.register(shutil.rmtree, directory, ignore_errors=True)  # the loaded .so stays mapped
-        (directory / "source.cu").write_text(code)
         try:
-            library = cabi.compile_library([directory / "source.cu"], directory / "library.so", command)
+            library = cabi.GnuLibrary(code, command, extension=".cu")
         except FileNotFoundError as error:
             raise cabi.CompilationError(f"compiler not found: {compiler}") from error
     _JIT_CACHE[key] = TypedLibrary(library)

@@ -10,7 +10,11 @@ Mirrors ``stencil_benchmarks/tools/compilation.py`` of the reference (file kept 
   STREAM hands back its table, stream/cuda_hip.py:121-144).
 * stdout/stderr are captured at file-descriptor level (compilation.py:54-86) so
   output written by C code is seen (``FdCapture``).
-* ``dtype_cname`` / ``data_ptr`` (compilation.py:254-282) keep their meaning.
+* ``GnuLibrary(code, compile_command, extension)`` compiles a source string and loads it as the
+  reference's class of that name does (compilation.py:89-153); ``dtype_as_ctype`` / ``ctype_cname`` /
+  ``dtype_cname`` / ``data_ptr`` (compilation.py:199-282) keep their meaning.  The reference's own unit
+  tests of these (test/tools/test_compilation.py) run against this module in
+  tests/test_sbench_dropin.py.
 
 Unlike ``GnuLibrary`` the library is pre-built in-tree by ``__graft_entry__.build()``
 (``nvcc -gencode arch=compute_100a,code=sm_100a``); ``compile_library`` offers the
@@ -149,22 +153,66 @@ def compile_library(
             "arch=compute_100a,code=sm_100a",
             "-lineinfo",
         ]
-    command = list(compile_command)
-    if command[0].endswith("nvcc"):
-        command += ["-Xcompiler", "-shared", "-Xcompiler", "-fPIC"]
-    else:
-        command += ["-shared", "-fPIC"]
-    result = subprocess.run(
-        [command[0], "-o", str(output)] + [str(s) for s in sources] + command[1:],
-        capture_output=True,
-    )
+    run_compiler(sources, output, list(compile_command))
+    return Library(output)
+
+
+def run_compiler(sources, output, command: List[str]) -> None:
+    """``[compiler, -o, output, sources...] + flags`` plus the shared-library flags of the compiler
+    family; raises ``CompilationError(stderr)``, warns about any other compiler output."""
+    shared = ["-Xcompiler", "-shared", "-Xcompiler", "-fPIC"] if command[0].endswith("nvcc") else ["-shared", "-fPIC"]
+    result = subprocess.run([command[0], "-o", str(output)] + [str(s) for s in sources] + command[1:] + shared,
+                            capture_output=True)
     if result.returncode != 0:
         raise CompilationError(result.stderr.decode())
     if result.stdout or result.stderr:
-        warnings.warn(
-            "unexpected compilation output: " + result.stdout.decode() + result.stderr.decode()
-        )
-    return Library(output)
+        warnings.warn("unexpected compilation output: " + result.stdout.decode() + result.stderr.decode())
+
+
+class GnuLibrary(Library):
+    """``GnuLibrary(code, compile_command, extension)`` of the reference (compilation.py:89-153) for a
+    machine without the reference package: the source string is written to
+    ``./benchmarks_source_code/`` (kept, as there), compiled into a scratch ``.so`` with
+    ``[compiler, -o, lib, src] + flags + -shared -fPIC`` (``-Xcompiler`` forms for nvcc) and
+    loaded; defaults: extension ``.cpp``, compiler ``gcc`` for ``.c`` and ``g++`` otherwise.
+    Compiler failure -> ``CompilationError(stderr)``, any compiler output -> a warning."""
+
+    def __init__(self, code: str, compile_command: Optional[List[str]] = None,
+                 extension: Optional[str] = None):
+        extension = extension or ".cpp"
+        if compile_command is None:
+            compile_command = ["gcc" if extension.lower() == ".c" else "g++"]
+        kept = pathlib.Path("benchmarks_source_code")
+        kept.mkdir(exist_ok=True)
+        handle, source = tempfile.mkstemp(suffix=extension, dir=kept)
+        with os.fdopen(handle, "w") as stream:
+            stream.write(code)
+        with tempfile.TemporaryDirectory(prefix="sb200_lib_") as scratch:
+            target = pathlib.Path(scratch) / "library.so"
+            run_compiler([source], target, list(compile_command))
+            super().__init__(target)  # stays mapped after the scratch directory is gone
+
+
+_CTYPES = {"f4": ctypes.c_float, "f8": ctypes.c_double}
+_CTYPES.update({f"{kind}{size}": getattr(ctypes, f"c_{'u' if kind == 'u' else ''}int{8 * size}")
+                for kind in "iu" for size in (1, 2, 4, 8)})
+
+
+def dtype_as_ctype(dtype):
+    """ctypes scalar type of a NumPy dtype (compilation.py:199-225)."""
+    dt = np.dtype(dtype)
+    try:
+        return _CTYPES[f"{dt.kind}{dt.itemsize}"]
+    except KeyError:
+        raise NotImplementedError(f"Conversion of type {dt} is not supported") from None
+
+
+def ctype_cname(ctype) -> str:
+    """C spelling of a ctypes scalar type (compilation.py:228-251)."""
+    for key, candidate in _CTYPES.items():
+        if candidate is ctype:
+            return dtype_cname(np.dtype(key))
+    raise NotImplementedError(f"Conversion of type {ctype} is not supported")
 
 
 _C_NAMES = {"f2": "half", "f4": "float", "f8": "double"}

@@ -219,3 +219,36 @@ print(checked)
     result = run(code, reference_path)
     assert result.returncode == 0, result.stderr[-3000:]
     assert int(result.stdout.strip().splitlines()[-1]) == 48
+
+
+def test_reference_unit_tests_pass_against_the_stand_alone_modules(tmp_path):
+    """Where the reference package is not importable (the GPU box) `benchmark.py`, `tools/fields.py`
+    and `tools/cabi.py` stand in for its `benchmark`, `tools.array` and `tools.compilation`.  The
+    reference's OWN unit tests of those modules -- unmodified, loaded from the reference tree --
+    must pass against the stand-ins (27 tests: plugin API, alloc_array, GnuLibrary and its helpers)."""
+    code = f"""
+import importlib.util, sys, types, unittest
+import stencil_benchmarks_b200.benchmark as benchmark
+assert not benchmark.HAVE_REFERENCE            # the reference is NOT on the path of this process
+from stencil_benchmarks_b200.tools import cabi, fields
+package = types.ModuleType("stencil_benchmarks"); package.__path__ = []
+tools = types.ModuleType("stencil_benchmarks.tools"); tools.__path__ = []
+package.benchmark, package.tools, tools.array, tools.compilation = benchmark, tools, fields, cabi
+sys.modules.update({{"stencil_benchmarks": package, "stencil_benchmarks.benchmark": benchmark,
+                    "stencil_benchmarks.tools": tools, "stencil_benchmarks.tools.array": fields,
+                    "stencil_benchmarks.tools.compilation": cabi}})
+suite = unittest.TestSuite()
+for index, relative in enumerate(["test_benchmark.py", "tools/test_array.py", "tools/test_compilation.py"]):
+    spec = importlib.util.spec_from_file_location(f"reference_test_{{index}}",
+                                                  {str(REFERENCE / "stencil_benchmarks" / "test")!r} + "/" + relative)
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    suite.addTests(unittest.defaultTestLoader.loadTestsFromModule(module))
+result = unittest.TextTestRunner(stream=sys.stderr, verbosity=0).run(suite)
+print(result.testsRun, len(result.failures), len(result.errors), len(result.skipped))
+"""
+    env = dict(os.environ, PYTHONPATH=str(ROOT))
+    result = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                            cwd=tmp_path)
+    assert result.returncode == 0, result.stderr[-3000:]
+    assert result.stdout.strip().splitlines()[-1] == "27 0 0 0", result.stderr[-3000:]
