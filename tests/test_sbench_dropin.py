@@ -252,3 +252,74 @@ print(result.testsRun, len(result.failures), len(result.errors), len(result.skip
                             cwd=tmp_path)
     assert result.returncode == 0, result.stderr[-3000:]
     assert result.stdout.strip().splitlines()[-1] == "27 0 0 0", result.stderr[-3000:]
+
+
+def test_stand_alone_stencil_definitions_equal_the_reference(reference_path, tmp_path):
+    """The stand-alone stencil base classes (used where the reference is absent) against the
+    reference's classes, live, on 60 random parameter sets: field names, data_size, strides, field
+    shapes, alignment of the first interior element, inner_slice -- and the same ParameterError
+    verdicts for halos the stencil cannot live with."""
+    code = f"""
+import sys
+import numpy as np
+import stencil_benchmarks_b200.benchmark as ours_benchmark
+assert not ours_benchmark.HAVE_REFERENCE
+import stencil_benchmarks_b200.benchmarks_collection.stencils.base as ours
+sys.path.insert(0, {reference_path!r})
+import stencil_benchmarks.benchmark as ref_benchmark
+import stencil_benchmarks.benchmarks_collection.stencils.base as ref
+
+def probe(cls):
+    class Probe(cls):
+        def run_stencil(self, data):
+            return dict(time=1.0)
+    return Probe
+
+def build(module, errors, name, kwargs):
+    try:
+        return probe(getattr(module, name))(**kwargs), None
+    except errors as error:
+        return None, type(error).__name__
+
+rng = np.random.default_rng(7)
+names = ["CopyStencil", "OnesidedAverageStencil", "SymmetricAverageStencil", "LaplacianStencil",
+         "HorizontalDiffusionStencil", "VerticalAdvectionStencil"]
+compared = refused = 0
+for n in range(60):
+    name = names[n % len(names)]
+    kwargs = dict(domain=tuple(int(v) for v in rng.integers(1, 40, 3)),
+                  halo=tuple(int(v) for v in rng.integers(0, 4, 3)),
+                  dtype=["float64", "float32"][int(rng.integers(0, 2))],
+                  alignment=int(rng.choice([0, 8, 64, 128, 12])), verify=False)
+    if "Average" in name:
+        kwargs["axis"] = int(rng.integers(0, 3))
+    if name == "LaplacianStencil":
+        kwargs.update(along_x=bool(rng.integers(0, 2)), along_y=bool(rng.integers(0, 2)), along_z=bool(rng.integers(0, 2)))
+    if name == "VerticalAdvectionStencil":
+        kwargs["all_components"] = bool(rng.integers(0, 2))
+    a, a_error = build(ours, (ours_benchmark.ParameterError,), name, kwargs)
+    b, b_error = build(ref, (ref_benchmark.ParameterError,), name, kwargs)
+    assert a_error == b_error, (name, kwargs, a_error, b_error)
+    if a is None:
+        refused += 1
+        continue
+    assert tuple(a.args) == tuple(b.args), (name, kwargs)
+    assert int(a.data_size) == int(b.data_size), (name, kwargs, a.data_size, b.data_size)
+    assert tuple(int(s) for s in a.strides) == tuple(int(s) for s in b.strides), (name, kwargs, a.strides, b.strides)
+    assert tuple(a.domain_with_halo) == tuple(b.domain_with_halo)
+    fa, fb = a._data[0][0], b._data[0][0]
+    assert fa.shape == fb.shape and fa.strides == fb.strides and fa.dtype == fb.dtype
+    if kwargs["alignment"]:
+        first = fa[tuple(slice(h, None) for h in kwargs["halo"])]
+        assert first.ctypes.data % kwargs["alignment"] == 0
+    assert a.inner_slice() == b.inner_slice() and a.inner_slice(shift=(1, 0, -1)) == b.inner_slice(shift=(1, 0, -1))
+    assert a.inner_slice(expand=(1, 1, 0)) == b.inner_slice(expand=(1, 1, 0))
+    compared += 1
+print(compared, refused)
+"""
+    env = dict(os.environ, PYTHONPATH=str(ROOT))
+    result = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                            cwd=tmp_path)
+    assert result.returncode == 0, result.stderr[-3000:]
+    compared, refused = (int(v) for v in result.stdout.split())
+    assert compared + refused == 60 and compared >= 25 and refused >= 5
