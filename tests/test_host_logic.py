@@ -402,3 +402,37 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     rows, segments, xtiles, ctas = (int(v) for v in run.stdout.split())
     assert rows == 32 and segments == 64 and xtiles == 8 and ctas == 8 * 64 * 80
     assert "multiple of 32" in run.stderr
+
+
+def test_stream_run_parses_the_mccalpin_table(monkeypatch):
+    """`stream b200 native`.run(): the library prints the reference's table (stream/cuda_hip.j2:
+    250-275), the plugin turns it into the reference's result dicts (stream/cuda_hip.py:127-144):
+    bandwidth in MB/s from the minimum time, avg / min / max time in seconds."""
+    table = ("Function    Best Rate MB/s  Avg time     Min time     Max time\n"
+             "Copy:         6921034.2     0.002490     0.002482     0.002511\n"
+             "Scale:        6913201.9     0.002491     0.002485     0.002500\n"
+             "Add:          7113400.0     0.003630     0.003623     0.003650\n"
+             "Triad:        7133020.5     0.003620     0.003613     0.003641\n")
+    calls = []
+
+    class Fake:
+        def sb200_set_device(self, device):
+            calls.append(("device", device))
+
+        def sb200_stream_configure(self, *args):
+            calls.append(("configure", args))
+
+        def sb200_stream_run(self, *args):
+            calls.append(("run", args))
+            return table
+
+    native = stream.Native(array_size=1 << 20, ntimes=7, dtype="float32", vector_size=8, unroll_factor=2,
+                           block_size=256, device=3)
+    monkeypatch.setattr(capi, "require_device", lambda: None)
+    native._lib = native._kernels = Fake()
+    results = native.run()
+    assert [r["name"] for r in results] == ["copy", "scale", "add", "triad"]
+    assert results[3] == {"name": "triad", "bandwidth": 7133020.5, "avg-time": 0.003620, "time": 0.003613,
+                          "max-time": 0.003641}
+    # vector_size is in elements (the reference's meaning): 8 floats = 32-byte vectors
+    assert calls == [("device", 3), ("configure", (256, 2, 32, 1)), ("run", (capi.F32, 1 << 20, 7, 1))]
