@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from oracle import native, stencils
-from stencil_benchmarks_b200 import capi
+from stencil_benchmarks_b200 import capi, distributed
 from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import (
     basic,
     horizontal_diffusion,
@@ -243,3 +243,82 @@ def test_vadv_run_moves_inputs_up_and_only_the_solution_down(device, chunks, all
     assert (device.h2d, device.d2h) == bench.transfer_bytes()
     moved_up = sum(1 for name in bench.args if bench.field_roles[name] in ("in", "inout"))
     assert moved_up == (13 if all_components else 5) and device.d2h < device.h2d
+
+
+# ---- the J-partitioned class: N emulated devices in one process --------------------------------------
+class FakePartitionDevice(FakeDevice):
+    """Adds what `Partitioned` needs: memset, peer access, and `sb200_hdiff_peer`, whose halo rows
+    come from the NEIGHBOURING slabs' memory (here: gathered into a scratch field for the oracle)."""
+
+    def __init__(self):
+        super().__init__()
+        self.peer_pairs = set()
+        self.devices_used = []
+
+    def sb200_set_device(self, device):
+        self.devices_used.append(device)
+        return 0
+
+    def sb200_memset(self, pointer, value, nbytes, stream, sync):
+        ctypes.memset(address(pointer), value, nbytes)
+        return 0
+
+    def sb200_enable_peer_access(self, device, peer):
+        self.peer_pairs.add((device, peer))
+        return 0
+
+    def sb200_event_destroy(self, event):
+        return 0
+
+    @staticmethod
+    def _rows(pointer, nx, first_row, rows, nz, sy, sz):
+        """Rows [first_row, first_row + rows) x i in [-2, nx + 2) x nz levels at `pointer` (interior origin)."""
+        base = address(pointer) + 8 * (first_row * sy - 2)
+        flat = np.ctypeslib.as_array((ctypes.c_double * 1).from_address(base))
+        return np.lib.stride_tricks.as_strided(flat, shape=(nx + 4, rows, nz), strides=(8, 8 * sy, 8 * sz))
+
+    def sb200_hdiff_peer(self, code, inp, coeff, out, lower, ny_lower, sz_lower, upper, ny_upper, sz_upper,
+                         nx, ny, nz, sx, sy, sz, dry_runs, time_pointer, stream):
+        assert sx == 1 and code == capi.F64
+        self.launches.append((ny, address(out)))
+        halo = (2, 2, 0)
+        field = np.zeros((nx + 4, ny + 4, nz), order="F")
+        field[:, 2:ny + 2, :] = self._rows(inp, nx, 0, ny, nz, sy, sz)
+        # a neighbour's slab supplies the two rows beyond the edge; at the global boundary they are local
+        field[:, :2, :] = (self._rows(lower, nx, ny_lower - 2, 2, nz, sy, sz_lower) if address(lower)
+                           else self._rows(inp, nx, -2, 2, nz, sy, sz))
+        field[:, ny + 2:, :] = (self._rows(upper, nx, 0, 2, nz, sy, sz_upper) if address(upper)
+                                else self._rows(inp, nx, ny, 2, nz, sy, sz))
+        weights = np.zeros_like(field)
+        weights[2:nx + 2, 2:ny + 2, :] = self._rows(coeff, nx, 0, ny, nz, sy, sz)[2:nx + 2]
+        result = np.zeros_like(field)
+        native.hdiff(field, weights, result, halo)
+        self._rows(out, nx, 0, ny, nz, sy, sz)[2:nx + 2] = result[2:nx + 2, 2:ny + 2, :]
+        self._finish(time_pointer)
+
+
+@pytest.mark.parametrize("gpus,domain", [(1, (20, 9, 3)), (2, (33, 17, 4)), (3, (20, 10, 2)), (4, (16, 8, 3))])
+def test_partitioned_class_scatters_sweeps_and_gathers(monkeypatch, gpus, domain):
+    fake = FakePartitionDevice()
+    monkeypatch.setattr(capi, "require_device", lambda: None)
+    monkeypatch.setattr(capi, "device_count", lambda: 8)
+    monkeypatch.setattr(capi, "DeviceBuffer", FakeBuffer)
+    monkeypatch.setattr(capi, "synchronize", lambda stream=None: None)
+    bench = on_fake_device(horizontal_diffusion.Partitioned, fake, domain=domain, gpus=gpus, device=2)
+    data = bench.data(0)
+    inp0, coeff0, out0 = (np.array(f, copy=True) for f in data)
+    expected = stencils.hdiff(inp0, coeff0, bench.halo)
+    result = bench.run()
+    inner = interior(bench)
+    # internal j-halo rows of the slabs are never uploaded (they stay 0xFF = NaN in "HBM"): equality
+    # with the oracle on the GLOBAL field shows the sweeps took them from the neighbouring slabs
+    np.testing.assert_array_equal(data.out[inner], expected[inner])
+    assert np.array_equal(data.inp, inp0) and np.array_equal(data.coeff, coeff0)
+    outside = np.ones(out0.shape, dtype=bool)
+    outside[inner] = False
+    assert np.array_equal(data.out[outside], out0[outside])
+    assert result["gpus"] == gpus and result["time"] > 0
+    assert sorted(rows for rows, _ in fake.launches) == sorted(
+        count for _, count in distributed.split_rows(domain[1], gpus))
+    assert set(fake.devices_used) == set(range(2, 2 + gpus))
+    assert fake.peer_pairs == {(a, b) for a in range(2, 2 + gpus) for b in (a - 1, a + 1) if 2 <= b < 2 + gpus}
