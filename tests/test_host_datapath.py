@@ -81,12 +81,13 @@ class FakeDevice:
     def _finish(time_pointer):
         if time_pointer is not None:
             time_pointer._obj.value = 1e-3
+        return 0  # status of the bare handle; callers of the wrapped form ignore it
 
     def sb200_hdiff(self, code, inp, coeff, out, nx, ny, nz, sx, sy, sz, dry_runs, time_pointer, stream):
         assert sx == 1 and code == capi.F64
         self.launches.append((ny, address(out)))
         native.lib().oracle_hdiff_f64(inp, coeff, out, I64(nx), I64(ny), I64(nz), I64(sy), I64(sz))
-        self._finish(time_pointer)
+        return self._finish(time_pointer)
 
     def sb200_basic(self, kind, code, inp, out, nx, ny, nz, sx, sy, sz, axis, mask, dry_runs, time_pointer, stream):
         assert sx == 1 and code == capi.F64
@@ -99,7 +100,7 @@ class FakeDevice:
         else:
             native.lib().oracle_average_f64(inp, out, *geometry, ctypes.c_int(axis),
                                             ctypes.c_int(int(kind == capi.BASIC_SYMMETRIC_AVG)))
-        self._finish(time_pointer)
+        return self._finish(time_pointer)
 
     def sb200_vadv_components(self, code, ncomp, stage, pos, tens, tensstage, ishift, jshift, wcon, ccol, dcol,
                               nx, ny, nz, sx, sy, sz, variant, dry_runs, time_pointer, stream):
@@ -110,7 +111,7 @@ class FakeDevice:
                 ctypes.c_void_p(stage[c]), ctypes.c_void_p(pos[c]), ctypes.c_void_p(tens[c]),
                 ctypes.c_void_p(tensstage[c]), wcon, ccol, dcol, I64(nx), I64(ny), I64(nz), I64(sy), I64(sz),
                 ctypes.c_int(ishift[c]), ctypes.c_int(jshift[c]))
-        self._finish(time_pointer)
+        return self._finish(time_pointer)
 
 
 class FakeBuffer:
@@ -294,7 +295,7 @@ class FakePartitionDevice(FakeDevice):
         result = np.zeros_like(field)
         native.hdiff(field, weights, result, halo)
         self._rows(out, nx, 0, ny, nz, sy, sz)[2:nx + 2] = result[2:nx + 2, 2:ny + 2, :]
-        self._finish(time_pointer)
+        return self._finish(time_pointer)
 
 
 @pytest.mark.parametrize("gpus,domain", [(1, (20, 9, 3)), (2, (33, 17, 4)), (3, (20, 10, 2)), (4, (16, 8, 3))])
@@ -322,3 +323,34 @@ def test_partitioned_class_scatters_sweeps_and_gathers(monkeypatch, gpus, domain
         count for _, count in distributed.split_rows(domain[1], gpus))
     assert set(fake.devices_used) == set(range(2, 2 + gpus))
     assert fake.peer_pairs == {(a, b) for a in range(2, 2 + gpus) for b in (a - 1, a + 1) if 2 <= b < 2 + gpus}
+
+
+def test_time_loop_alternates_the_two_buffers(device, monkeypatch):
+    """distributed.TimeLoop on one (emulated) device: sweep m reads X_m and writes X_(m+1), the two
+    buffers alternate, the halo keeps its values -- equal to the oracle applied again and again."""
+
+    def memcpy_d2d(dst, src, nbytes, stream, sync):
+        ctypes.memmove(address(dst), address(src), nbytes)
+        return 0
+
+    def memset(pointer, value, nbytes, stream, sync):
+        ctypes.memset(address(pointer), value, nbytes)
+        return 0
+
+    device.sb200_memcpy_d2d, device.sb200_memset = memcpy_d2d, memset
+    monkeypatch.setattr(capi, "library", lambda: device)
+    bench = on_fake_device(horizontal_diffusion.Fused, device, domain=(24, 15, 3))
+    data = bench.data(0)
+    data.coeff[...] *= 0.025  # a stable time step (bench.TIME_LOOP_COEFF_SCALE)
+    mirrors = bench._device_fields(data)
+    bench.upload(data, mirrors)
+    loop = distributed.TimeLoop(bench, mirrors)
+    state = np.array(data.inp, copy=True)
+    inner = interior(bench)
+    for sweep in range(1, 6):
+        loop.step()
+        state[inner] = stencils.hdiff(state, np.array(data.coeff), bench.halo)[inner]
+        got = loop.download(bench.empty_field())
+        np.testing.assert_array_equal(got, state, err_msg=f"after sweep {sweep}")
+    assert loop.count == 5 and len({out for _, out in device.launches}) == 2
+    loop.close()
