@@ -354,3 +354,28 @@ def test_time_loop_alternates_the_two_buffers(device, monkeypatch):
         np.testing.assert_array_equal(got, state, err_msg=f"after sweep {sweep}")
     assert loop.count == 5 and len({out for _, out in device.launches}) == 2
     loop.close()
+
+
+def test_data_sets_cycle_with_their_own_mirrors(device):
+    """`data_sets` (base.py:47-51, :152): run() cycles through independent field sets; every set has
+    its own device mirrors, allocated once, and every sweep lands in the set it belongs to."""
+    bench = on_fake_device(basic.Laplacian, device, domain=(12, 9, 4), halo=(1, 1, 1), data_sets=3)
+    expected = [stencils.laplacian(np.array(bench.data(n).inp), bench.halo) for n in range(3)]
+    for _ in range(5):
+        bench.run()
+    inner = interior(bench)
+    for n in range(3):
+        np.testing.assert_array_equal(bench.data(n).out[inner], expected[n][inner])
+    assert len(bench._device) == 3 and len(device.launches) == 5
+    # three distinct output mirrors were written: sets 0 and 1 twice, set 2 once
+    written = [out for _, out in device.launches]
+    assert len(set(written)) == 3 and written[0] == written[3] and written[1] == written[4]
+
+
+def test_wall_timer_and_dry_runs(device):
+    bench = on_fake_device(basic.Copy, device, domain=(10, 6, 3), halo=(0, 0, 0), timers="wall", dry_runs=2)
+    result = bench.run()
+    assert result["time"] > 0 and result["bandwidth"] > 0
+    np.testing.assert_array_equal(bench.data(0).out, bench.data(0).inp)
+    # two C calls: the warm-up call (which the library repeats dry_runs times) and the wall-timed one
+    assert len(device.launches) == 2
