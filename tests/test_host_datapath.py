@@ -379,3 +379,53 @@ def test_wall_timer_and_dry_runs(device):
     np.testing.assert_array_equal(bench.data(0).out, bench.data(0).inp)
     # two C calls: the warm-up call (which the library repeats dry_runs times) and the wall-timed one
     assert len(device.launches) == 2
+
+
+@pytest.mark.parametrize("gpus", [1, 2, 3, 5])
+@pytest.mark.parametrize("case", [
+    (basic.PartitionedCopy, {}, lambda f, h: stencils.copy(f, h)),
+    (basic.PartitionedOnesidedAverage, dict(axis=1), lambda f, h: stencils.onesided_average(f, h, 1)),
+    (basic.PartitionedSymmetricAverage, dict(axis=1), lambda f, h: stencils.symmetric_average(f, h, 1)),
+    (basic.PartitionedSymmetricAverage, dict(axis=2), lambda f, h: stencils.symmetric_average(f, h, 2)),
+    (basic.PartitionedLaplacian, dict(along_x=True, along_y=True, along_z=True),
+     lambda f, h: stencils.laplacian(f, h, (True, True, True))),
+], ids=["copy", "onesided_j", "symmetric_j", "symmetric_k", "laplacian_ijk"])
+def test_partitioned_basic_stencils(monkeypatch, gpus, case):
+    """The basic stencils over 1-5 emulated devices: the j halo of a slab (rows of the neighbouring
+    slabs) arrives with the scatter; gathered result equal to the oracle on the global field."""
+    cls, parameters, oracle = case
+    fake = FakePartitionDevice()
+    monkeypatch.setattr(capi, "require_device", lambda: None)
+    monkeypatch.setattr(capi, "device_count", lambda: 8)
+    monkeypatch.setattr(capi, "DeviceBuffer", FakeBuffer)
+    monkeypatch.setattr(capi, "synchronize", lambda stream=None: None)
+    bench = on_fake_device(cls, fake, domain=(19, 11, 4), halo=(1, 1, 2), gpus=gpus, device=1, **parameters)
+    data = bench.data(0)
+    inp0, out0 = np.array(data.inp, copy=True), np.array(data.out, copy=True)
+    expected = oracle(inp0, bench.halo)
+    result = bench.run()
+    inner = interior(bench)
+    np.testing.assert_array_equal(data.out[inner], expected[inner])
+    assert np.array_equal(data.inp, inp0)
+    outside = np.ones(out0.shape, dtype=bool)
+    outside[inner] = False
+    assert np.array_equal(data.out[outside], out0[outside])
+    assert result["gpus"] == gpus and result["time"] > 0 and "bandwidth" in result
+    assert sorted(rows for rows, _ in fake.launches) == sorted(n for _, n in distributed.split_rows(11, gpus))
+    assert set(fake.devices_used) == set(range(1, 1 + gpus))
+    bench.run()  # buffers and events are allocated once
+    assert len(fake.launches) == 2 * gpus and fake.handles == 2 * gpus
+
+
+def test_partitioned_basic_parameter_errors():
+    from stencil_benchmarks_b200.benchmark import ParameterError
+
+    kwargs = dict(pinned=False, verify=False, domain=(8, 3, 2))
+    with pytest.raises(ParameterError, match="at least one row"):
+        basic.PartitionedCopy(gpus=4, **kwargs)
+    with pytest.raises(ParameterError, match="gpus must be at least 1"):
+        basic.PartitionedCopy(gpus=0, **kwargs)
+    with pytest.raises(ParameterError, match="chunks / resident"):
+        basic.PartitionedLaplacian(gpus=2, chunks=2, **kwargs)
+    with pytest.raises(ParameterError, match="positive halo"):
+        basic.PartitionedOnesidedAverage(gpus=2, axis=1, halo=(1, 0, 1), **kwargs)

@@ -39,6 +39,8 @@ def test_registered_command_names():
         "stencils b200 basic laplacian", "stencils b200 horizontal-diffusion fused",
         "stencils b200 horizontal-diffusion partitioned",
         "stencils b200 vertical-advection thomas", "stream b200 native",
+        "stencils b200 basic partitioned-copy", "stencils b200 basic partitioned-onesided-average",
+        "stencils b200 basic partitioned-symmetric-average", "stencils b200 basic partitioned-laplacian",
     }
 
 
