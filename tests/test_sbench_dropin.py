@@ -323,3 +323,64 @@ print(compared, refused)
     assert result.returncode == 0, result.stderr[-3000:]
     compared, refused = (int(v) for v in result.stdout.split())
     assert compared + refused == 60 and compared >= 25 and refused >= 5
+
+
+def test_reference_run_and_oracle_judge_the_backend_classes_on_an_emulated_device(reference_path):
+    """The plugin contract under the REAL reference, without a GPU: with `stencil_benchmarks`
+    importable the backend classes are driven by the reference's own `Stencil.run()` and judged by its
+    `verify_stencil` (base.py:151-166) -- results written back into the host fields before returning,
+    inputs bit-unchanged, a positive `time` and no `bandwidth` key.  The device is emulated
+    (tests/test_host_datapath.py), so this checks the wiring, not the kernels; the same test runs
+    with real kernels on the GPU box (tests/test_gpu_dropin.py)."""
+    code = f"""
+import sys
+sys.path.insert(0, {str(ROOT / "tests")!r})
+import numpy as np
+import stencil_benchmarks.benchmark as ref
+from stencil_benchmarks.benchmarks_collection.stencils import base as ref_base
+import test_host_datapath as emulated
+from stencil_benchmarks_b200 import capi
+from stencil_benchmarks_b200.benchmarks_collection.stencils.b200 import basic, horizontal_diffusion, vertical_advection
+
+fake = emulated.FakePartitionDevice()
+capi.require_device = lambda: None
+capi.device_count = lambda: 8
+capi.DeviceBuffer = emulated.FakeBuffer
+capi.synchronize = lambda stream=None: None
+import ctypes
+capi.memcpy_h2d = lambda d, h, n, stream=None, sync=True: ctypes.memmove(d, h, n)
+capi.memcpy_d2h = lambda h, d, n, stream=None, sync=True: ctypes.memmove(h, d, n)
+
+cases = [
+    (horizontal_diffusion.Fused, dict(domain=(21, 14, 4))),
+    (horizontal_diffusion.Fused, dict(domain=(21, 14, 4), chunks=3)),
+    (horizontal_diffusion.Partitioned, dict(domain=(21, 14, 4), gpus=2)),
+    (vertical_advection.Thomas, dict(domain=(12, 9, 7))),
+    (vertical_advection.Thomas, dict(domain=(12, 9, 7), all_components=True, chunks=2)),
+    (basic.Laplacian, dict(domain=(15, 8, 5), along_z=True)),
+    (basic.OnesidedAverage, dict(domain=(15, 8, 5), axis=1, chunks=2)),
+    (basic.PartitionedLaplacian, dict(domain=(15, 8, 5), gpus=3)),
+    (basic.PartitionedSymmetricAverage, dict(domain=(15, 8, 5), axis=1, gpus=2)),
+]
+for cls, kwargs in cases:
+    assert issubclass(cls, ref.Benchmark) and cls.run is ref_base.Stencil.run
+    bench = cls(pinned=False, verify=True, **kwargs)        # verify=True: the reference's default
+    bench._lib = bench._kernels = fake
+    result = bench.run()                                     # raises if verify_stencil finds a difference
+    assert result["time"] > 0 and result["bandwidth"] > 0
+# negative control: a sweep that is not executed must be rejected by the reference's validation
+class Idle(emulated.FakePartitionDevice):
+    def sb200_hdiff(self, *args):
+        return self._finish(args[-2])   # reports a time, computes nothing
+bench = horizontal_diffusion.Fused(pinned=False, verify=True, domain=(21, 14, 4))
+bench._lib = bench._kernels = Idle()
+import stencil_benchmarks.tools.validation as validation
+try:
+    bench.run()
+except validation.ValidationError as error:
+    print("rejected:", str(error).splitlines()[0])
+print(len(cases))
+"""
+    result = run(code, reference_path)
+    assert result.returncode == 0, result.stderr[-3000:]
+    assert result.stdout.strip().splitlines()[-2:] == ["rejected: validation of field out failed", "9"]
