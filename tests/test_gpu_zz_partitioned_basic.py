@@ -3,7 +3,8 @@
 The host logic (scatter with the neighbours' rows as j halo, one sweep per device, gather) is
 covered on emulated devices in tests/test_host_datapath.py; here the same classes run on real
 devices: on one GPU (`gpus=1`, any box) and on every pair / all GPUs of a multi-GPU box.
-(The file sorts after the other GPU tests on purpose: it was added last.)
+(The file sorts after the other GPU tests on purpose: it was added last; first GPU run:
+profiles/gputests_partitioned_basic_r02.log.)
 """
 
 import numpy as np
