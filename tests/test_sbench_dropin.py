@@ -385,3 +385,43 @@ print(len(cases))
     assert result.returncode == 0, result.stderr[-3000:]
     lines = result.stdout.strip().splitlines()
     assert lines[-1] == "9" and lines[-2].startswith("rejected: validation of field out failed at 1176 points")
+
+
+def test_reference_cli_drives_the_backend_on_an_emulated_device(reference_path, tmp_path):
+    """`sbench -e 2 -o out.csv stencils b200 ...` through the reference's click tree (cli.py:47-73; the
+    reference's own CLI test does the same with its numpy backend, test/test_cli.py:38-54), range
+    syntax and CSV writer included, verification on (the default) -- on the emulated device."""
+    import pandas as pd
+
+    code = f"""
+import ctypes, sys
+sys.path.insert(0, {str(ROOT / "tests")!r})
+import stencil_benchmarks.benchmarks_collection
+import stencil_benchmarks_b200.benchmarks_collection
+import test_host_datapath as emulated
+from stencil_benchmarks_b200 import capi
+from stencil_benchmarks import cli
+fake = emulated.FakePartitionDevice()
+capi.require_device = lambda: None
+capi.device_count = lambda: 8
+capi.library = lambda: fake
+capi.DeviceBuffer = emulated.FakeBuffer
+capi.synchronize = lambda stream=None: None
+capi.memcpy_h2d = lambda d, h, n, stream=None, sync=True: ctypes.memmove(d, h, n)
+capi.memcpy_d2h = lambda h, d, n, stream=None, sync=True: ctypes.memmove(h, d, n)
+cli.main(args=sys.argv[1:], standalone_mode=False)
+"""
+    out = tmp_path / "hdiff.csv"
+    result = run(code, reference_path, "--executions", "2", "--output", str(out), "stencils", "b200",
+                 "horizontal-diffusion", "fused", "--domain", "10", "10", "10", "--no-pinned", "--chunks", "[1,2]")
+    assert result.returncode == 0, result.stdout + result.stderr[-3000:]
+    table = pd.read_csv(out)
+    assert len(table) == 4 and sorted(set(table["chunks"])) == [1, 2]
+    assert (table["bandwidth"] > 0).all() and table["verify"].all()
+    assert {"time", "bandwidth-algorithmic", "alignment", "sbench-version"} <= set(table.columns)
+
+    out = tmp_path / "partitioned.csv"
+    result = run(code, reference_path, "--executions", "1", "--output", str(out), "stencils", "b200", "basic",
+                 "partitioned-laplacian", "--domain", "12", "9", "4", "--no-pinned", "--gpus", "[1,3]", "--along-z")
+    assert result.returncode == 0, result.stdout + result.stderr[-3000:]
+    assert list(pd.read_csv(out)["gpus"]) == [1, 3]
