@@ -13,7 +13,7 @@ from .... import capi
 from ....benchmark import ExecutionError, Parameter, ParameterError
 from ....tools import cabi
 from .. import base
-from .mixin import StencilMixin, _vp
+from .mixin import SlabCopies, StencilMixin, _vp
 
 
 class HorizontalDiffusionMixin(StencilMixin):
@@ -89,7 +89,7 @@ class Fused(HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
     alignment = Parameter("data alignment in bytes", 128)
 
 
-class Partitioned(HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
+class Partitioned(SlabCopies, HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
     """Horizontal diffusion of ONE domain partitioned over ``gpus`` GPUs, driven by this process
     (``sbench stencils b200 horizontal-diffusion partitioned --gpus 8``).
 
@@ -168,26 +168,6 @@ class Partitioned(HorizontalDiffusionMixin, base.HorizontalDiffusionStencil):
         lib.sb200_set_device(self.device)
         self._slabs = slabs
         return slabs
-
-    def _copy_rows(self, slab, host, name, first_row, rows, to_device, planes):
-        """Padded rows [first_row, first_row + rows) of the slab, `planes` = (first, count) levels."""
-        size = host.itemsize
-        sy, sz_host = int(self.strides[1]), int(self.strides[2])
-        k0, nk = planes
-        h_off = ((slab["start"] + first_row) * sy + k0 * sz_host) * size
-        d_off = (first_row * sy + k0 * slab["sz"]) * size
-        copy = self._lib.sb200_memcpy2d_h2d if to_device else self._lib.sb200_memcpy2d_d2h
-        if to_device:
-            copy(_vp(slab["first"][name] + d_off), slab["sz"] * size, _vp(host.ctypes.data + h_off),
-                 sz_host * size, rows * sy * size, nk, None)
-        else:
-            copy(_vp(host.ctypes.data + h_off), sz_host * size, _vp(slab["first"][name] + d_off),
-                 slab["sz"] * size, rows * sy * size, nk, None)
-
-    def _sync_all(self, slabs):
-        for slab in slabs:
-            self._lib.sb200_set_device(slab["device"])
-            capi.synchronize()
 
     def run_stencil(self, data):
         try:

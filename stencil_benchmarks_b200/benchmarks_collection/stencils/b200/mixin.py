@@ -352,3 +352,29 @@ class StencilMixin(Benchmark):
         """(nx, ny, nz, sx, sy, sz) as the C ABI expects them (element strides)."""
         domain = self.domain if domain is None else domain
         return tuple(int(d) for d in domain) + tuple(int(s) for s in self.strides)
+
+
+class SlabCopies:
+    """Copies between the host fields of a GLOBAL domain and the J slabs a process keeps on several
+    devices (the ``partitioned`` benchmark classes).  A slab is a dict with ``device``, ``start``
+    (first global row), ``sz`` (its level pitch in elements) and ``first[name]`` (device address of
+    element 0 of the field's slab); rows keep the host's pitch."""
+
+    def _copy_rows(self, slab, host, name, first_row, rows, to_device, planes):
+        """Padded rows [first_row, first_row + rows) of the slab, `planes` = (first, count) levels."""
+        size = host.itemsize
+        sy, sz_host = int(self.strides[1]), int(self.strides[2])
+        k0, nk = planes
+        h_off = ((slab["start"] + first_row) * sy + k0 * sz_host) * size
+        d_off = (first_row * sy + k0 * slab["sz"]) * size
+        if to_device:
+            self._lib.sb200_memcpy2d_h2d(_vp(slab["first"][name] + d_off), slab["sz"] * size,
+                                         _vp(host.ctypes.data + h_off), sz_host * size, rows * sy * size, nk, None)
+        else:
+            self._lib.sb200_memcpy2d_d2h(_vp(host.ctypes.data + h_off), sz_host * size,
+                                         _vp(slab["first"][name] + d_off), slab["sz"] * size, rows * sy * size, nk, None)
+
+    def _sync_all(self, slabs):
+        for slab in slabs:
+            self._lib.sb200_set_device(slab["device"])
+            capi.synchronize()
